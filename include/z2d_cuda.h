@@ -1,0 +1,243 @@
+/*
+ * z2d_cuda.h -- C ABI of the B200-native fill/stroke rasterise-and-composite
+ * library (libz2d_cuda.so).
+ *
+ * This is the drop-in boundary for the one hot path of vancluever/z2d that this
+ * repository re-implements: everything below z2d's unmanaged painter /
+ * compositor entry points.  Each entry point names the reference interface it
+ * replaces (file:line relative to the z2d tree).  All types are plain C PODs;
+ * enum values follow the declaration order of the reference's Zig enums so a
+ * Zig shim can pass `@intFromEnum(x)` straight through.
+ *
+ * Calls are stream-ordered and asynchronous unless stated otherwise; draw
+ * calls are recorded into a per-context command batch and executed, in
+ * submission order, at the next flush point (z2d_flush, z2d_sync,
+ * z2d_surface_download, z2d_composite on the same context, or when the batch
+ * is full).  Results are identical to executing every call immediately.
+ *
+ * Threading: a z2d_ctx is single-threaded (as z2d's Context is); distinct
+ * contexts may be used from distinct threads.
+ */
+#ifndef Z2D_CUDA_H
+#define Z2D_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (reference: painter.zig:54-63,204-209; surface.zig:85-91;
+ *      Transformation.zig:26-28; internal/InternalError.zig) ---------------- */
+enum {
+  Z2D_OK = 0,
+  Z2D_E_PATH_NOT_CLOSED = -1,               /* FillError.PathNotClosed */
+  Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED = -2, /* PixelSourceNotPreMultiplied */
+  Z2D_E_INVALID_WIDTH = -3,                 /* Surface.Error.InvalidWidth */
+  Z2D_E_INVALID_HEIGHT = -4,                /* Surface.Error.InvalidHeight */
+  Z2D_E_INVALID_STATE = -5,                 /* InternalError.InvalidState */
+  Z2D_E_OUT_OF_MEMORY = -6,                 /* mem.Allocator.Error */
+  Z2D_E_INVALID_MATRIX = -7,                /* Transformation.Error.InvalidMatrix */
+  Z2D_E_DEVICE = -8,                        /* CUDA / NCCL failure (new) */
+  Z2D_E_INVALID_ARG = -9                    /* NULL handle, bad enum (new) */
+};
+
+/* pixel.Format (pixel.zig:47-56) */
+enum {
+  Z2D_FMT_ARGB = 0, Z2D_FMT_XRGB = 1, Z2D_FMT_RGB = 2, Z2D_FMT_RGBA = 3,
+  Z2D_FMT_ALPHA8 = 4, Z2D_FMT_ALPHA4 = 5, Z2D_FMT_ALPHA2 = 6, Z2D_FMT_ALPHA1 = 7
+};
+
+/* compositor.Operator (compositor.zig:46-155) */
+enum {
+  Z2D_OP_CLEAR = 0, Z2D_OP_SRC, Z2D_OP_DST, Z2D_OP_SRC_OVER, Z2D_OP_DST_OVER,
+  Z2D_OP_SRC_IN, Z2D_OP_DST_IN, Z2D_OP_SRC_OUT, Z2D_OP_DST_OUT, Z2D_OP_SRC_ATOP,
+  Z2D_OP_DST_ATOP, Z2D_OP_XOR, Z2D_OP_PLUS, Z2D_OP_MULTIPLY, Z2D_OP_SCREEN,
+  Z2D_OP_OVERLAY, Z2D_OP_DARKEN, Z2D_OP_LIGHTEN, Z2D_OP_COLOR_DODGE,
+  Z2D_OP_COLOR_BURN, Z2D_OP_HARD_LIGHT, Z2D_OP_SOFT_LIGHT, Z2D_OP_DIFFERENCE,
+  Z2D_OP_EXCLUSION, Z2D_OP_HUE, Z2D_OP_SATURATION, Z2D_OP_COLOR,
+  Z2D_OP_LUMINOSITY, Z2D_OP_COUNT
+};
+
+/* compositor.Precision (compositor.zig:214-217) */
+enum { Z2D_PRECISION_INTEGER = 0, Z2D_PRECISION_FLOAT = 1 };
+
+/* options.zig:23-91 */
+enum { Z2D_FILL_NON_ZERO = 0, Z2D_FILL_EVEN_ODD = 1 };
+enum { Z2D_JOIN_MITER = 0, Z2D_JOIN_ROUND = 1, Z2D_JOIN_BEVEL = 2 };
+enum { Z2D_CAP_BUTT = 0, Z2D_CAP_ROUND = 1, Z2D_CAP_SQUARE = 2 };
+enum { Z2D_AA_NONE = 0, Z2D_AA_DEFAULT = 1, Z2D_AA_MULTISAMPLE_4X = 2, Z2D_AA_SUPERSAMPLE_4X = 3 };
+
+/* internal/path_nodes.zig:9-21 -- PathNodeTag.  Points are DEVICE space
+ * (the CTM was already applied by Path.zig:124-145). */
+enum { Z2D_NODE_MOVE_TO = 0, Z2D_NODE_LINE_TO = 1, Z2D_NODE_CURVE_TO = 2, Z2D_NODE_CLOSE_PATH = 3 };
+
+typedef struct z2d_node {
+  uint32_t tag;
+  uint32_t _pad;
+  double p[6]; /* move/line: p[0..1]; curve: p1=(p[0],p[1]) p2=(p[2],p[3]) p3=(p[4],p[5]) */
+} z2d_node;   /* 56 bytes */
+
+/* pixel.Pixel (pixel.zig:100-140): channel values as stored by the format
+ * (alpha4: a in 0..15, alpha2: 0..3, alpha1: 0..1). */
+typedef struct z2d_pixel {
+  uint32_t format;
+  uint8_t r, g, b, a;
+} z2d_pixel;
+
+/* color.Color (color.zig:40-70): de-multiplied colour in one of three spaces. */
+enum { Z2D_COLOR_LINEAR_RGB = 0, Z2D_COLOR_SRGB = 1, Z2D_COLOR_HSL = 2 };
+typedef struct z2d_color {
+  uint32_t space;
+  float c[4]; /* r,g,b,a or h,s,l,a -- already clamped as Color.init does */
+} z2d_color;
+
+/* gradient.Stop (gradient.zig:776-781); the list is sorted as Stop.List keeps
+ * it (offset ascending, ties by insertion index, gradient.zig:797-811). */
+typedef struct z2d_stop {
+  float offset;
+  z2d_color color;
+} z2d_stop;
+
+/* gradient.GradientType; color.InterpolationMethod (+ Polar) */
+enum { Z2D_GRADIENT_LINEAR = 0, Z2D_GRADIENT_RADIAL = 1, Z2D_GRADIENT_CONIC = 2 };
+enum { Z2D_INTERP_LINEAR_RGB = 0, Z2D_INTERP_SRGB = 1, Z2D_INTERP_HSL = 2 };
+enum { Z2D_POLAR_SHORTER = 0, Z2D_POLAR_LONGER = 1, Z2D_POLAR_INCREASING = 2, Z2D_POLAR_DECREASING = 3 };
+
+/* gradient.Gradient (gradient.zig:31-160).
+ *   linear: geom = {x0,y0,x1,y1}
+ *   radial: geom = {inner_x,inner_y,inner_r,outer_x,outer_y,outer_r}
+ *   conic : geom = {x,y,angle}
+ * inv_ctm is the *stored* transformation of the gradient, i.e. the inverse of
+ * the CTM passed to setTransformation (gradient.zig:201-203), laid out as
+ * {ax,by,cx,dy,tx,ty}; identity when no transformation was set. */
+typedef struct z2d_gradient {
+  uint32_t type;
+  uint32_t method;
+  uint32_t polar;
+  uint32_t n_stops;
+  double geom[6];
+  double inv_ctm[6];
+  const z2d_stop* stops;
+} z2d_gradient;
+
+/* Dither (Dither.zig:28-58) */
+enum { Z2D_DITHER_NONE = 0, Z2D_DITHER_BAYER = 1, Z2D_DITHER_BLUE_NOISE = 2 };
+enum { Z2D_DITHER_SRC_PIXEL = 0, Z2D_DITHER_SRC_COLOR = 1, Z2D_DITHER_SRC_GRADIENT = 2 };
+
+/* pattern.Pattern (pattern.zig:32-44) */
+enum { Z2D_PATTERN_OPAQUE = 0, Z2D_PATTERN_GRADIENT = 1, Z2D_PATTERN_DITHER = 2 };
+typedef struct z2d_pattern {
+  uint32_t kind;
+  z2d_pixel pixel;              /* OPAQUE; DITHER with SRC_PIXEL */
+  const z2d_gradient* gradient; /* GRADIENT; DITHER with SRC_GRADIENT */
+  uint32_t dither_type;         /* DITHER */
+  uint32_t dither_source;
+  uint32_t dither_scale;        /* Dither.scale (u4), Context.zig:690-695 */
+  z2d_color dither_color;       /* DITHER with SRC_COLOR */
+} z2d_pattern;
+
+/* painter.FillOptions (painter.zig:28-48) */
+typedef struct z2d_fill_opts {
+  uint32_t anti_aliasing_mode;
+  uint32_t fill_rule;
+  uint32_t op;
+  uint32_t precision;
+  double tolerance;
+} z2d_fill_opts;
+
+/* painter.StrokeOptions (painter.zig:145-198) */
+typedef struct z2d_stroke_opts {
+  uint32_t anti_aliasing_mode;
+  uint32_t line_cap_mode;
+  uint32_t line_join_mode;
+  uint32_t op;
+  uint32_t precision;
+  uint32_t hairline;
+  double line_width;
+  double miter_limit;
+  double tolerance;
+  double dash_offset;
+  const double* dashes;
+  size_t n_dashes;
+  double ctm[6]; /* {ax,by,cx,dy,tx,ty} */
+} z2d_stroke_opts;
+
+typedef struct z2d_ctx z2d_ctx; /* device + stream + command batch */
+typedef struct z2d_sfc z2d_sfc; /* device-resident surface */
+
+/* compositor.SurfaceCompositor.Operation.Param (compositor.zig:232-283) */
+enum { Z2D_PARAM_NONE = 0, Z2D_PARAM_DITHER = 1, Z2D_PARAM_GRADIENT = 2, Z2D_PARAM_PIXEL = 3, Z2D_PARAM_SURFACE = 4 };
+typedef struct z2d_comp_param {
+  uint32_t kind;
+  z2d_pattern pattern;   /* PIXEL / GRADIENT / DITHER expressed as a pattern */
+  const void* surface;   /* SURFACE: a z2d_sfc* (device library) */
+} z2d_comp_param;
+
+/* compositor.SurfaceCompositor.Operation (compositor.zig:220-230) */
+typedef struct z2d_comp_op {
+  uint32_t op;
+  z2d_comp_param dst;
+  z2d_comp_param src;
+} z2d_comp_op;
+
+/* ------------------------------------------------------------------------- */
+
+/* Library / context ------------------------------------------------------- */
+int32_t z2d_version(void);                      /* ABI version, currently 1 */
+const char* z2d_last_error(const z2d_ctx* ctx); /* text of the last Z2D_E_DEVICE */
+
+/* One context per device/thread.  `stream` is a cudaStream_t or NULL for a
+ * private non-blocking stream.  (No reference equivalent: z2d has no device.) */
+int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out);
+void z2d_ctx_destroy(z2d_ctx* ctx);
+int32_t z2d_flush(z2d_ctx* ctx); /* enqueue everything recorded so far */
+int32_t z2d_sync(z2d_ctx* ctx);  /* flush + wait */
+
+/* Surface (surface.zig:97-186 init/initPixel/initBuffer, 188 deinit).
+ * Byte layout of upload/download == the reference's `buf` slices: tightly
+ * packed w*h pixels, 4 B for argb/xrgb/rgb/rgba, 1 B alpha8, and
+ * bit-contiguous LSB-first alpha4/2/1 with rows NOT byte aligned
+ * (surface.zig:632,756-765).  initial_px may be NULL (zeroed). */
+int32_t z2d_surface_create(z2d_ctx* ctx, uint32_t format, int32_t width, int32_t height,
+                           const z2d_pixel* initial_px, z2d_sfc** out);
+void z2d_surface_destroy(z2d_sfc* sfc);
+size_t z2d_surface_byte_len(const z2d_sfc* sfc);
+int32_t z2d_surface_width(const z2d_sfc* sfc);
+int32_t z2d_surface_height(const z2d_sfc* sfc);
+uint32_t z2d_surface_format(const z2d_sfc* sfc);
+int32_t z2d_surface_upload(z2d_sfc* sfc, const void* host, size_t n);
+int32_t z2d_surface_download(z2d_sfc* sfc, void* host, size_t n); /* flushes + syncs */
+void* z2d_surface_device_ptr(z2d_sfc* sfc); /* raw device pointer (interop) */
+/* Surface.paintPixel (surface.zig:295) */
+int32_t z2d_surface_paint_pixel(z2d_sfc* sfc, const z2d_pixel* px);
+
+/* painter.fill (painter.zig:66-143) */
+int32_t z2d_fill(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,
+                 const z2d_node* nodes, size_t n_nodes, const z2d_fill_opts* opts);
+
+/* painter.stroke (painter.zig:214-344) */
+int32_t z2d_stroke(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,
+                   const z2d_node* nodes, size_t n_nodes, const z2d_stroke_opts* opts);
+
+/* compositor.SurfaceCompositor.run (compositor.zig:302-440).  Infallible in
+ * the reference (invalid combinations are silent no-ops); the status only
+ * reports device/argument errors. */
+int32_t z2d_composite(z2d_ctx* ctx, z2d_sfc* dst, int32_t dst_x, int32_t dst_y,
+                      const z2d_comp_op* ops, size_t n_ops, uint32_t precision);
+
+/* Statistics of the last flushed batch (counters the benchmark reports). */
+typedef struct z2d_stats {
+  uint64_t draws;        /* fill/stroke calls executed */
+  uint64_t edges;        /* flattened polygon edges */
+  uint64_t tile_items;   /* (draw, tile) pairs rasterised */
+  uint64_t crossings;    /* edge x sub-scanline evaluations (upper bound) */
+  uint64_t kernel_launches;
+} z2d_stats;
+int32_t z2d_get_stats(const z2d_ctx* ctx, z2d_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Z2D_CUDA_H */
