@@ -212,6 +212,8 @@ int32_t z2d_surface_download(z2d_sfc* sfc, void* host, size_t n); /* flushes + s
 void* z2d_surface_device_ptr(z2d_sfc* sfc); /* raw device pointer (interop) */
 /* Surface.paintPixel (surface.zig:295) */
 int32_t z2d_surface_paint_pixel(z2d_sfc* sfc, const z2d_pixel* px);
+/* Surface.putPixel (surface.zig:288): out-of-bounds coordinates are ignored */
+int32_t z2d_surface_put_pixel(z2d_sfc* sfc, int32_t x, int32_t y, const z2d_pixel* px);
 
 /* painter.fill (painter.zig:66-143) */
 int32_t z2d_fill(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,

@@ -28,6 +28,14 @@ int32_t z2d_ref_surface_paint_pixel(void* buf, uint32_t fmt, int32_t w, int32_t 
   return Z2D_OK;
 }
 
+// Surface.putPixel (surface.zig:288, 519, 769)
+int32_t z2d_ref_surface_put_pixel(void* buf, uint32_t fmt, int32_t w, int32_t h, int32_t x, int32_t y, const z2d_pixel* px) {
+  if (x < 0 || y < 0 || x >= w || y >= h) return Z2D_OK;
+  Sfc s{(uint8_t*)buf, fmt, w, h};
+  sfc_paint(s, (size_t)w * (size_t)y + (size_t)x, *px);
+  return Z2D_OK;
+}
+
 static int check_pattern(const z2d_pattern* p) {  // painter.zig:73-79
   if (p->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(p->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
   return Z2D_OK;

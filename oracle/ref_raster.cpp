@@ -341,7 +341,7 @@ void raster_supersample(Sfc& s, const Src& pat, Polygon& poly, uint32_t rule, ui
   int bx1 = clampi(x1 * scale, bx0, tws - 1), by1 = clampi(y1 * scale, by0, ths - 1);
   int mw = (bx1 + 1) - bx0, mh = (by1 + 1) - by0;
   if (mw < 1 || mh < 1) return;
-  uint32_t mfmt = (s.fmt == Z2D_FMT_ALPHA4 || s.fmt == Z2D_FMT_ALPHA2 || s.fmt == Z2D_FMT_ALPHA1) ? s.fmt : Z2D_FMT_ALPHA8;
+  uint32_t mfmt = (s.fmt == Z2D_FMT_ALPHA4 || s.fmt == Z2D_FMT_ALPHA2 || s.fmt == Z2D_FMT_ALPHA1) ? s.fmt : (uint32_t)Z2D_FMT_ALPHA8;
   z2d_pixel opaque_px{mfmt, 0, 0, 0, (uint8_t)(mfmt == Z2D_FMT_ALPHA8 ? 255 : mfmt == Z2D_FMT_ALPHA4 ? 15 : mfmt == Z2D_FMT_ALPHA2 ? 3 : 1)};
   std::vector<uint8_t> mbuf(sfc_byte_len(mfmt, mw, mh), 0);
   Sfc mask{mbuf.data(), mfmt, mw, mh};

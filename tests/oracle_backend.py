@@ -35,6 +35,8 @@ def load_oracle(fast=False):
     lib.z2d_ref_surface_byte_len.argtypes = [C.c_uint32, C.c_int32, C.c_int32]
     lib.z2d_ref_surface_paint_pixel.restype = C.c_int32
     lib.z2d_ref_surface_paint_pixel.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, P(abi.PixelPOD)]
+    lib.z2d_ref_surface_put_pixel.restype = C.c_int32
+    lib.z2d_ref_surface_put_pixel.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(abi.PixelPOD)]
     lib.z2d_ref_fill.restype = C.c_int32
     lib.z2d_ref_fill.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]
     lib.z2d_ref_stroke.restype = C.c_int32
@@ -85,6 +87,9 @@ class OracleBackend:
 
     def surface_paint_pixel(self, hd, px):
         abi.check(self.lib.z2d_ref_surface_paint_pixel(hd.ptr, hd.fmt, hd.w, hd.h, C.byref(px.pod())))
+
+    def surface_put_pixel(self, hd, x, y, px):
+        abi.check(self.lib.z2d_ref_surface_put_pixel(hd.ptr, hd.fmt, hd.w, hd.h, x, y, C.byref(px.pod())))
 
     def surface_param(self, hd, keep):
         rs = RefSurface(hd.buf.ctypes.data, hd.fmt, hd.w, hd.h)

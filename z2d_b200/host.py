@@ -273,6 +273,8 @@ class Path:
         ip = self.initial_point
         self.nodes.append((NodeTag.move_to, ip[0], ip[1], 0.0, 0.0, 0.0, 0.0))
 
+    close_path = close
+
     def is_closed(self):
         return is_closed_node_set(self.nodes)
 
@@ -595,6 +597,9 @@ class Surface:
 
     def paint_pixel(self, px):  # surface.zig:295
         self.backend.surface_paint_pixel(self.handle, px)
+
+    def put_pixel(self, x, y, px):  # surface.zig:288
+        self.backend.surface_put_pixel(self.handle, int(x), int(y), px)
 
     def composite(self, src, operator, dst_x, dst_y, precision=Precision.integer):  # surface.zig:225-241
         SurfaceCompositor.run(self, dst_x, dst_y, [Operation(operator, src=Param.surface(src))], precision)
