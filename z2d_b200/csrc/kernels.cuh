@@ -1,0 +1,59 @@
+// Kernel argument blocks and launch wrappers (implemented in kernels.cu).
+#pragma once
+#include "z2d_batch.cuh"
+
+namespace z2d {
+
+constexpr int kRasterThreads = 256;  // 8 warps = 8 tiles per CTA
+constexpr uint32_t kDrawChunk = 256; // draws per band-list work item
+constexpr uint32_t kMaxCompOps = 8;
+
+struct RasterArgs {
+  const DevSurface* sfcs;
+  uint32_t n_sfc;
+  uint32_t n_tiles;
+  const uint32_t* work_base;   // per surface: first band-list work item
+  const uint32_t* list_off;    // per work item (+1): offset into list_items
+  const uint2* list_items;     // (draw index, tx0 | tx1 << 16), draw order within a tile-row
+  const DevDraw* draws;
+  const uint32_t* band_off;    // per (draw, tile-row) slot (+1): offset into band_edges
+  const DevEdge* band_edges;
+  GradTables T;
+};
+
+struct CompOp {
+  uint32_t op, has_dst, has_src, _pad;
+  DevSrc dst, src;
+};
+
+struct CompArgs {  // SurfaceCompositor.run after clipping (compositor.zig:347-388)
+  uint8_t* data;
+  uint32_t fmt;
+  int32_t w, h;
+  int32_t dst_start_x, dst_start_y, src_start_x, src_start_y;
+  int32_t scan_w, rows;
+  uint32_t n_ops, precision;
+  GradTables T;
+  CompOp ops[kMaxCompOps];
+};
+
+size_t scan_tmp_len(uint32_t n);
+// out[0..n) = exclusive scan of in[0..n), out[n] = total
+void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
+
+void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, cudaStream_t st);
+void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
+                         DevEdge* edges, uint32_t* edge_draw, cudaStream_t st);
+void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, cudaStream_t st);
+void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, cudaStream_t st);
+void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
+void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
+                        uint32_t* band_cursor, DevEdge* band_edges, cudaStream_t st);
+void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
+                       const DevDraw* draws, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
+void launch_raster(const RasterArgs& A, cudaStream_t st);
+void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st);
+void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st);
+void launch_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t raw, cudaStream_t st);
+
+}  // namespace z2d

@@ -1,0 +1,101 @@
+// Batch data model shared by the host recorder (z2d_lib.cu) and the kernels.
+//
+// A *batch* is the ordered list of painter.fill / painter.stroke calls recorded
+// since the last flush.  It is rendered by a fixed kernel pipeline:
+//
+//   K1 flatten_count  one thread per sub-path: nodes -> #edges, extents   (fill_plotter / Spline / Polygon.addEdge)
+//   K1 flatten_emit   same walk, writes edges {y0,y1,x_start,x_inc}
+//   K2 setup_draws    one thread per draw: extents -> pixel region, tile range   (multisample.zig:38-78 etc.)
+//   K3 bin_edges      edges -> per (draw, tile-row) lists (count / scan / scatter; order-free)
+//   K3 band_lists     per tile-row of each surface: ordered list of the draws touching it (count / scan / write)
+//   K4 raster_tiles   one warp per 16x16-pixel tile: walks its draws IN SUBMISSION ORDER, evaluates the
+//                     4x4 sample coverage of each from the binned edges and composites into the
+//                     register-resident tile; the tile is read once and written once per batch.
+#pragma once
+#include <string.h>
+
+#include "z2d_device.cuh"
+
+namespace z2d {
+
+constexpr int kTile = 16;          // tile edge in pixels
+constexpr int kTileShift = 4;
+
+struct DevSurface {
+  uint8_t* data;
+  uint32_t fmt;
+  int32_t w, h;
+  int32_t tiles_x, tiles_y;
+  uint32_t tile_base;   // first global tile index of this surface in the batch
+  uint32_t band_base;   // first global tile-row ("band") index
+  uint32_t draw_begin, draw_end;  // draws of this surface (draws are grouped by surface, order preserved)
+};
+
+struct DevSubPath {  // one move_to ... run of nodes (state resets at every move_to)
+  uint32_t draw;
+  uint32_t node_begin, node_end;  // [begin,end) in the batch node array
+  uint32_t last_of_draw;          // 1 if node_end is the end of the draw's node list
+};
+
+struct DevDraw {
+  // --- recorded on the host
+  uint32_t surface;
+  uint32_t kind;       // 0 fill, 1 stroke
+  uint32_t aa;         // effective AA mode: Z2D_AA_NONE / MULTISAMPLE_4X / SUPERSAMPLE_4X
+  uint32_t rule, op, precision;  // precision already upgraded when the operator requires float
+  uint32_t reduces;    // shared.zig:111-117 fillReducesToSource
+  uint32_t paint_raw;  // T.fromPixel(source pixel) for the surface format (opaque fast path)
+  double scale, tolerance;
+  DevSrc src;
+  // stroke parameters (painter.zig:287-304 already applied)
+  uint32_t cap, join;
+  double thickness, miter_limit, dash_offset;
+  double ctm[6];
+  uint32_t dash_begin, dash_count;
+  uint32_t pen_begin, pen_count;
+  // --- produced on the device
+  long long ext[4];    // order-encoded f64: top(min) bottom(max) left(min) right(max)
+  uint32_t n_edges;
+  uint32_t valid;
+  int32_t rx0, rx1, ry0, ry1;   // pixel region whose coverage is evaluated: [rx0,rx1) x [ry0,ry1)
+  int32_t tx0, tx1, ty0, ty1;   // tile range (inclusive) the draw touches
+  int32_t ey0, ey1;             // tile-row range (inclusive) of the evaluated region (edge binning)
+  int32_t pre_y0, pre_y1, pre_x, pre_rows;  // MSAA unbounded pre-clear (multisample.zig:96-110)
+  uint32_t band_base;           // first (draw, tile-row) slot
+  uint32_t unbounded;
+};
+
+struct DevEdge {
+  double y0, y1, x_start, x_inc;
+};
+
+// order-preserving f64 <-> i64 (for atomicMin / atomicMax on extents)
+Z2D_HD long long f64_order(double v) {
+  long long b;
+#ifdef __CUDA_ARCH__
+  b = __double_as_longlong(v);
+#else
+  memcpy(&b, &v, 8);
+#endif
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+Z2D_HD double f64_unorder(long long k) {
+  long long b = k >= 0 ? k : (k ^ 0x7fffffffffffffffLL);
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+// Zig @round on f64: half away from zero; exact (v - trunc(v) is exact)
+Z2D_HD double round_half_away(double v) {
+  double t = trunc(v);
+  double f = v - t;
+  if (fabs(f) >= 0.5) t += (v < 0.0 ? -1.0 : 1.0);
+  return t;
+}
+
+}  // namespace z2d

@@ -1,0 +1,857 @@
+// C ABI of libz2d_cuda.so (include/z2d_cuda.h): contexts, device-resident
+// surfaces, the draw-call recorder and the batch pipeline driver.
+//
+// Host work on the boundary is limited to what painter.fill / painter.stroke do
+// before tessellation (argument validation, AA-mode selection, option clamping:
+// painter.zig:66-104, 214-304), splitting the node list into sub-paths and
+// converting gradient stops to their interpolation space once per call
+// (the reference redoes that per pixel, color_vector.zig:197-207).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "blue_noise_table.h"
+#include "kernels.cuh"
+
+using namespace z2d;
+
+namespace {
+
+struct DevBuf {  // growable device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 4096;
+    while (ncap < bytes) ncap = ncap + ncap / 2 + 4096;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, ncap);
+    if (e == cudaSuccess) cap = ncap;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+template <class T>
+struct PinnedVec {  // growable pinned host array (async H2D source)
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t ncap = cap ? cap : 1024;
+    while (ncap < want) ncap *= 2;
+    T* np = nullptr;
+    if (cudaHostAlloc((void**)&np, ncap * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+    if (n) memcpy(np, p, n * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = ncap;
+    return true;
+  }
+  bool append(const T* src, size_t k) {
+    if (!reserve(n + k)) return false;
+    memcpy(p + n, src, k * sizeof(T));
+    n += k;
+    return true;
+  }
+  bool push(const T& v) { return append(&v, 1); }
+  void clear() { n = 0; }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = cap = 0;
+  }
+};
+
+}  // namespace
+
+struct z2d_sfc {
+  z2d_ctx* ctx;
+  uint8_t* data;
+  uint32_t fmt;
+  int32_t w, h;
+  size_t bytes;
+  int32_t batch_slot;  // index in the current batch's surface table, or -1
+};
+
+struct z2d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string last_error;
+  z2d_stats stats{};
+
+  // recorded batch
+  PinnedVec<z2d_node> nodes;
+  PinnedVec<DevSubPath> subpaths;
+  PinnedVec<DevDraw> draws;
+  std::vector<z2d_sfc*> batch_sfcs;
+  std::vector<DevGrad> grads;
+  std::vector<float> stop_offsets;
+  std::vector<float4> stop_colors;
+
+  // device state
+  DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
+  DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
+  DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
+  DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
+  uint32_t* h_total = nullptr;  // pinned readback slot
+};
+
+namespace {
+
+int fail(z2d_ctx* c, const char* what, cudaError_t e) {
+  if (c) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    c->last_error = buf;
+  }
+  return Z2D_E_DEVICE;
+}
+#define CK(c, call)                              \
+  do {                                           \
+    cudaError_t _e = (call);                     \
+    if (_e != cudaSuccess) return fail(c, #call, _e); \
+  } while (0)
+
+// ---------------------------------------------------------------- colour (host)
+// color.zig:166-195,408-478 -- conversions of gradient stops into the interpolation space.
+struct F4 {
+  float r, g, b, a;
+};
+const float kGammaH = 2.2f;
+float zmodf_h(float a, float b) {
+  float r = std::fmod(a, b);
+  if (r < 0) r += b;
+  return r;
+}
+float hsl_channel_h(float n, float hue, float sat, float light) {
+  float k = std::fmod(n + hue / 30.0f, 12.0f);
+  float a = sat * std::min(light, 1.0f - light);
+  return light - a * std::max(-1.0f, std::min(std::min(k - 3.0f, 9.0f - k), 1.0f));
+}
+F4 hsl_to_rgb_h(F4 h) {
+  float hue = std::fmod(h.r, 360.0f);
+  if (hue < 0) hue += 360.0f;
+  return {hsl_channel_h(0, hue, h.g, h.b), hsl_channel_h(8, hue, h.g, h.b), hsl_channel_h(4, hue, h.g, h.b), h.a};
+}
+F4 hsl_from_rgb_h(F4 s) {
+  float mx = std::max(s.r, std::max(s.g, s.b)), mn = std::min(s.r, std::min(s.g, s.b));
+  float range = mx - mn, light = (mn + mx) / 2;
+  float sat = (light == 0 || light == 1) ? 0 : (mx - light) / std::min(light, 1 - light);
+  float hue = 0;
+  if (range != 0) {
+    if (mx == s.r) hue = 60 * zmodf_h((s.g - s.b) / range, 6);
+    else if (mx == s.g) hue = 60 * ((s.b - s.r) / range + 2);
+    else if (mx == s.b) hue = 60 * ((s.r - s.g) / range + 4);
+  }
+  if (sat < 0) {
+    hue += 180;
+    if (hue >= 360) hue -= 360;
+    sat = std::fabs(sat);
+  }
+  return {hue, sat, light, s.a};
+}
+F4 color_to_linear_h(const z2d_color& c) {
+  F4 v{c.c[0], c.c[1], c.c[2], c.c[3]};
+  if (c.space == Z2D_COLOR_LINEAR_RGB) return v;
+  if (c.space == Z2D_COLOR_SRGB) return {std::pow(v.r, kGammaH), std::pow(v.g, kGammaH), std::pow(v.b, kGammaH), v.a};
+  return hsl_to_rgb_h(v);
+}
+F4 color_to_srgb_h(const z2d_color& c) {
+  F4 v{c.c[0], c.c[1], c.c[2], c.c[3]};
+  if (c.space == Z2D_COLOR_SRGB) return v;
+  F4 lin = (c.space == Z2D_COLOR_LINEAR_RGB) ? v : hsl_to_rgb_h(v);
+  const float inv = 1 / kGammaH;
+  return {std::pow(lin.r, inv), std::pow(lin.g, inv), std::pow(lin.b, inv), lin.a};
+}
+F4 color_to_hsl_h(const z2d_color& c) {
+  if (c.space == Z2D_COLOR_HSL) return {c.c[0], c.c[1], c.c[2], c.c[3]};
+  return hsl_from_rgb_h(color_to_linear_h(c));
+}
+
+// Gradient.init + Radial/Conic pre-calculation (gradient.zig:262-300, 689)
+uint32_t add_gradient(const z2d_gradient& g, std::vector<DevGrad>& grads, std::vector<float>& offs, std::vector<float4>& cols) {
+  DevGrad o{};
+  o.type = g.type;
+  o.method = g.method;
+  o.polar = g.polar;
+  o.n_stops = g.n_stops;
+  o.stop_base = (uint32_t)offs.size();
+  for (int i = 0; i < 6; i++) {
+    o.geom[i] = g.geom[i];
+    o.inv[i] = g.inv_ctm[i];
+  }
+  o.inv_identity = (g.inv_ctm[0] == 1 && g.inv_ctm[1] == 0 && g.inv_ctm[2] == 0 && g.inv_ctm[3] == 1 && g.inv_ctm[4] == 0 && g.inv_ctm[5] == 0);
+  if (g.type == Z2D_GRADIENT_RADIAL) {
+    o.inner_r = std::max(0.0, g.geom[2]);
+    o.outer_r = std::max(0.0, g.geom[5]);
+    o.cdx = g.geom[3] - g.geom[0];
+    o.cdy = g.geom[4] - g.geom[1];
+    o.dr = o.outer_r - o.inner_r;
+    o.min_dr = -o.inner_r;
+    double a = 0;
+    a += o.cdx * o.cdx;
+    a += o.cdy * o.cdy;
+    a += o.dr * -o.dr;
+    o.a = a;
+    o.inv_a = (a != 0) ? 1 / a : 0;
+  } else if (g.type == Z2D_GRADIENT_CONIC) {
+    const double two_pi = M_PI * 2;
+    double r = std::fmod(g.geom[2], two_pi);
+    if (r < 0) r += two_pi;
+    o.geom[2] = r;
+  }
+  for (uint32_t i = 0; i < g.n_stops; i++) {
+    const z2d_color& c = g.stops[i].color;
+    F4 v = g.method == Z2D_INTERP_LINEAR_RGB ? color_to_linear_h(c) : g.method == Z2D_INTERP_SRGB ? color_to_srgb_h(c) : color_to_hsl_h(c);
+    offs.push_back(g.stops[i].offset);
+    cols.push_back(make_float4(v.r, v.g, v.b, v.a));
+  }
+  grads.push_back(o);
+  return (uint32_t)grads.size() - 1;
+}
+
+bool px_can_demultiply(const z2d_pixel& px) {  // pixel.zig:504-514
+  if (px.format != Z2D_FMT_ARGB && px.format != Z2D_FMT_RGBA) return true;
+  if (px.a == 0) return true;
+  return px.r * 255 / px.a <= 255 && px.g * 255 / px.a <= 255 && px.b * 255 / px.a <= 255;
+}
+bool px_is_opaque(const z2d_pixel& px) {  // pixel.zig:128-137
+  switch (px.format) {
+    case Z2D_FMT_XRGB: case Z2D_FMT_RGB: return true;
+    case Z2D_FMT_ARGB: case Z2D_FMT_RGBA: case Z2D_FMT_ALPHA8: return px.a == 255;
+    case Z2D_FMT_ALPHA4: return px.a == 15;
+    case Z2D_FMT_ALPHA2: return px.a == 3;
+    default: return px.a == 1;
+  }
+}
+
+int pattern_to_src(const z2d_pattern& p, DevSrc& s, std::vector<DevGrad>& grads, std::vector<float>& offs, std::vector<float4>& cols) {
+  memset(&s, 0, sizeof s);
+  auto set_pixel = [&](const z2d_pixel& px) {
+    RGBA16 v = pixel_to_rgba16(px.format, px.r, px.g, px.b, px.a);
+    s.px_rgba = (uint32_t)v.r | ((uint32_t)v.g << 8) | ((uint32_t)v.b << 16) | ((uint32_t)v.a << 24);
+    s.px_format = px.format;
+    s.px_raw = (uint32_t)px.r | ((uint32_t)px.g << 8) | ((uint32_t)px.b << 16) | ((uint32_t)px.a << 24);
+    return v;
+  };
+  switch (p.kind) {
+    case Z2D_PATTERN_OPAQUE:
+      if (p.pixel.format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
+      s.kind = Z2D_PARAM_PIXEL;
+      set_pixel(p.pixel);
+      return Z2D_OK;
+    case Z2D_PATTERN_GRADIENT:
+      if (!p.gradient) return Z2D_E_INVALID_ARG;
+      s.kind = Z2D_PARAM_GRADIENT;
+      s.grad = add_gradient(*p.gradient, grads, offs, cols);
+      return Z2D_OK;
+    case Z2D_PATTERN_DITHER:
+      s.kind = Z2D_PARAM_DITHER;
+      s.dither_type = p.dither_type;
+      s.dither_source = p.dither_source;
+      s.dither_scale = p.dither_scale;
+      if (p.dither_source == Z2D_DITHER_SRC_GRADIENT) {
+        if (!p.gradient) return Z2D_E_INVALID_ARG;
+        s.grad = add_gradient(*p.gradient, grads, offs, cols);
+      } else if (p.dither_source == Z2D_DITHER_SRC_COLOR) {
+        F4 c = color_to_linear_h(p.dither_color);
+        s.dcol[0] = c.r; s.dcol[1] = c.g; s.dcol[2] = c.b; s.dcol[3] = c.a;
+      } else {  // LinearRGB.decodeRGBA (color.zig:204-212): integer de-multiply, then /255
+        RGBA16 v = set_pixel(p.pixel);
+        if (v.a == 0) v = {0, 0, 0, 0};
+        else v = {v.r * 255 / v.a, v.g * 255 / v.a, v.b * 255 / v.a, v.a};
+        s.dcol[0] = (float)v.r / 255.0f; s.dcol[1] = (float)v.g / 255.0f; s.dcol[2] = (float)v.b / 255.0f; s.dcol[3] = (float)v.a / 255.0f;
+      }
+      return Z2D_OK;
+    default: return Z2D_E_INVALID_ARG;
+  }
+}
+
+cudaError_t upload(z2d_ctx* c, DevBuf& b, const void* src, size_t bytes) {
+  cudaError_t e = b.ensure(bytes ? bytes : 16);
+  if (e != cudaSuccess) return e;
+  if (bytes) return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream);
+  return cudaSuccess;
+}
+
+int read_total(z2d_ctx* c, const uint32_t* dev, uint32_t& out) {
+  CK(c, cudaMemcpyAsync(c->h_total, dev, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  out = *c->h_total;
+  return Z2D_OK;
+}
+
+void clear_batch(z2d_ctx* c) {
+  c->nodes.clear();
+  c->subpaths.clear();
+  c->draws.clear();
+  for (z2d_sfc* s : c->batch_sfcs) s->batch_slot = -1;
+  c->batch_sfcs.clear();
+  c->grads.clear();
+  c->stop_offsets.clear();
+  c->stop_colors.clear();
+}
+
+GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& sc) {
+  GradTables T;
+  T.grads = g.as<DevGrad>();
+  T.stop_offsets = so.as<float>();
+  T.stop_colors = sc.as<float4>();
+  T.blue_noise = c->d_blue.as<uint16_t>();
+  return T;
+}
+
+// ------------------------------------------------------------------ the pipeline
+int flush_impl(z2d_ctx* c) {
+  const uint32_t n_draws = (uint32_t)c->draws.n;
+  if (n_draws == 0) {
+    clear_batch(c);
+    return Z2D_OK;
+  }
+  cudaStream_t st = c->stream;
+  const uint32_t n_sfc = (uint32_t)c->batch_sfcs.size();
+
+  // 1. group draws by surface, keeping submission order inside each surface (draws on
+  //    different surfaces are independent), and build the surface / work tables.
+  std::vector<uint32_t> per_sfc(n_sfc + 1, 0), remap(n_draws);
+  for (uint32_t i = 0; i < n_draws; i++) per_sfc[c->draws.p[i].surface + 1]++;
+  for (uint32_t s = 0; s < n_sfc; s++) per_sfc[s + 1] += per_sfc[s];
+  std::vector<DevDraw> sorted(n_draws);
+  {
+    std::vector<uint32_t> cur(per_sfc.begin(), per_sfc.end() - 1);
+    for (uint32_t i = 0; i < n_draws; i++) {
+      uint32_t k = cur[c->draws.p[i].surface]++;
+      remap[i] = k;
+      sorted[k] = c->draws.p[i];
+    }
+  }
+  for (size_t i = 0; i < c->subpaths.n; i++) c->subpaths.p[i].draw = remap[c->subpaths.p[i].draw];
+  memcpy(c->draws.p, sorted.data(), sizeof(DevDraw) * n_draws);
+
+  std::vector<DevSurface> sfcs(n_sfc);
+  std::vector<uint32_t> work_base(n_sfc + 1, 0);
+  uint32_t n_tiles = 0;
+  for (uint32_t s = 0; s < n_sfc; s++) {
+    z2d_sfc* hs = c->batch_sfcs[s];
+    DevSurface& d = sfcs[s];
+    d.data = hs->data;
+    d.fmt = hs->fmt;
+    d.w = hs->w;
+    d.h = hs->h;
+    d.tiles_x = (hs->w + kTile - 1) / kTile;
+    d.tiles_y = (hs->h + kTile - 1) / kTile;
+    d.tile_base = n_tiles;
+    d.band_base = 0;
+    d.draw_begin = per_sfc[s];
+    d.draw_end = per_sfc[s + 1];
+    n_tiles += (uint32_t)d.tiles_x * (uint32_t)d.tiles_y;
+    const uint32_t chunks = (d.draw_end - d.draw_begin + kDrawChunk - 1) / kDrawChunk;
+    work_base[s + 1] = work_base[s] + (uint32_t)d.tiles_y * chunks;
+  }
+  const uint32_t n_work = work_base[n_sfc];
+  const uint32_t n_sp = (uint32_t)c->subpaths.n;
+
+  // 2. upload the batch
+  CK(c, upload(c, c->d_nodes, c->nodes.p, c->nodes.n * sizeof(z2d_node)));
+  CK(c, upload(c, c->d_subpaths, c->subpaths.p, c->subpaths.n * sizeof(DevSubPath)));
+  CK(c, upload(c, c->d_draws, c->draws.p, c->draws.n * sizeof(DevDraw)));
+  CK(c, upload(c, c->d_sfcs, sfcs.data(), sfcs.size() * sizeof(DevSurface)));
+  CK(c, upload(c, c->d_work_base, work_base.data(), work_base.size() * 4));
+  CK(c, upload(c, c->d_grads, c->grads.data(), c->grads.size() * sizeof(DevGrad)));
+  CK(c, upload(c, c->d_stop_off, c->stop_offsets.data(), c->stop_offsets.size() * 4));
+  CK(c, upload(c, c->d_stop_col, c->stop_colors.data(), c->stop_colors.size() * sizeof(float4)));
+
+  uint32_t launches = 0;
+  auto scan = [&](DevBuf& in, DevBuf& out, uint32_t n) -> cudaError_t {
+    cudaError_t e = out.ensure(((size_t)n + 1) * 4);
+    if (e != cudaSuccess) return e;
+    e = c->d_scan_tmp.ensure(scan_tmp_len(n) * 4);
+    if (e != cudaSuccess) return e;
+    exclusive_scan(in.as<uint32_t>(), out.as<uint32_t>(), n, c->d_scan_tmp.as<uint32_t>(), st);
+    launches += 3;
+    return cudaGetLastError();
+  };
+
+  // 3. K1: flatten (count, scan, emit)
+  CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
+  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(), st);
+  CK(c, scan(c->d_sp_count, c->d_sp_off, n_sp));
+  uint32_t n_edges = 0;
+  {
+    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
+    if (rc) return rc;
+  }
+  CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
+  CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
+  launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
+                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), st);
+
+  // 4. K2: per-draw regions; (draw, tile-row) slots
+  CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
+  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(), st);
+  CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
+  uint32_t n_slots = 0;
+  {
+    int rc = read_total(c, c->d_draw_band_off.as<uint32_t>() + n_draws, n_slots);
+    if (rc) return rc;
+  }
+  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), st);
+
+  // 5. K3a: edges -> (draw, tile-row) lists
+  CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
+  CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
+  CK(c, cudaMemsetAsync(c->d_band_count.p, 0, (size_t)n_slots * 4 + 16, st));
+  CK(c, cudaMemsetAsync(c->d_band_cursor.p, 0, (size_t)n_slots * 4 + 16, st));
+  launch_bin_count(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_count.as<uint32_t>(), st);
+  CK(c, scan(c->d_band_count, c->d_band_off, n_slots));
+  uint32_t n_band_edges = 0;
+  {
+    int rc = read_total(c, c->d_band_off.as<uint32_t>() + n_slots, n_band_edges);
+    if (rc) return rc;
+  }
+  CK(c, c->d_band_edges.ensure((size_t)n_band_edges * sizeof(DevEdge) + 32));
+  launch_bin_scatter(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_off.as<uint32_t>(),
+                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), st);
+
+  // 6. K3b: ordered draw list per surface tile-row
+  CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
+  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(),
+                    c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
+  CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
+  uint32_t n_items = 0;
+  {
+    int rc = read_total(c, c->d_list_off.as<uint32_t>() + n_work, n_items);
+    if (rc) return rc;
+  }
+  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
+  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(), nullptr,
+                    c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
+
+  // 7. K4: fused coverage + compositing
+  RasterArgs A;
+  A.sfcs = c->d_sfcs.as<DevSurface>();
+  A.n_sfc = n_sfc;
+  A.n_tiles = n_tiles;
+  A.work_base = c->d_work_base.as<uint32_t>();
+  A.list_off = c->d_list_off.as<uint32_t>();
+  A.list_items = c->d_list_items.as<uint2>();
+  A.draws = c->d_draws.as<DevDraw>();
+  A.band_off = c->d_band_off.as<uint32_t>();
+  A.band_edges = c->d_band_edges.as<DevEdge>();
+  A.T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
+  launch_raster(A, st);
+  CK(c, cudaGetLastError());
+  launches += 8;
+
+  c->stats.draws = n_draws;
+  c->stats.edges = n_edges;
+  c->stats.tile_items = n_items;
+  c->stats.crossings = n_band_edges;
+  c->stats.kernel_launches = launches;
+  clear_batch(c);
+  return Z2D_OK;
+}
+
+int flush(z2d_ctx* c) {
+  int rc = flush_impl(c);
+  if (rc != Z2D_OK) clear_batch(c);
+  return rc;
+}
+
+uint32_t batch_slot(z2d_ctx* c, z2d_sfc* s) {
+  if (s->batch_slot < 0) {
+    s->batch_slot = (int32_t)c->batch_sfcs.size();
+    c->batch_sfcs.push_back(s);
+  }
+  return (uint32_t)s->batch_slot;
+}
+
+bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23-37
+  if (n == 0) return false;
+  bool closed = false;
+  for (size_t i = 0; i < n; i++) {
+    if (nodes[i].tag == Z2D_NODE_MOVE_TO) {
+      if (!closed && i != 0) break;
+    } else if (nodes[i].tag == Z2D_NODE_CLOSE_PATH) {
+      closed = true;
+    } else {
+      closed = false;
+    }
+  }
+  return closed;
+}
+
+// Split the node list at every move_to and append nodes + sub-path records to the batch.
+int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n) {
+  // leading nodes before the first move_to: line_to / curve_to have no current point
+  // (fill_plotter.zig:50,53 -> InternalError.InvalidState); a leading close_path is a no-op.
+  size_t first = 0;
+  while (first < n && nodes[first].tag != Z2D_NODE_MOVE_TO) {
+    if (nodes[first].tag == Z2D_NODE_LINE_TO || nodes[first].tag == Z2D_NODE_CURVE_TO) return Z2D_E_INVALID_STATE;
+    if (nodes[first].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+    first++;
+  }
+  const uint32_t base = (uint32_t)c->nodes.n;
+  if (!c->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
+  const size_t m = n - first;
+  size_t i = 0;
+  while (i < m) {
+    size_t j = i + 1;
+    while (j < m && nodes[first + j].tag != Z2D_NODE_MOVE_TO) {
+      if (nodes[first + j].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+      j++;
+    }
+    DevSubPath sp;
+    sp.draw = draw_index;
+    sp.node_begin = base + (uint32_t)i;
+    sp.node_end = base + (uint32_t)j;
+    sp.last_of_draw = (j == m) ? 1u : 0u;
+    if (j - i > 1 && !c->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;  // a lone move_to draws nothing
+    i = j;
+  }
+  return Z2D_OK;
+}
+
+constexpr size_t kMaxBatchNodes = 8u << 20;   // flush thresholds (bounds pinned + device scratch)
+constexpr size_t kMaxBatchDraws = 1u << 20;
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int32_t z2d_version(void) { return 1; }
+
+const char* z2d_last_error(const z2d_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
+  if (!out) return Z2D_E_INVALID_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return Z2D_E_DEVICE;
+  z2d_ctx* c = new z2d_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return Z2D_E_DEVICE;
+    }
+    c->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
+      cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+    delete c;
+    return Z2D_E_DEVICE;
+  }
+  *out = c;
+  return Z2D_OK;
+}
+
+void z2d_ctx_destroy(z2d_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  clear_batch(c);
+  DevBuf* bufs[] = {&c->d_blue, &c->d_nodes, &c->d_subpaths, &c->d_draws, &c->d_sfcs, &c->d_grads, &c->d_stop_off, &c->d_stop_col,
+                    &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
+                    &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
+                    &c->d_scan_tmp, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col};
+  for (DevBuf* b : bufs) b->release();
+  c->nodes.release();
+  c->subpaths.release();
+  c->draws.release();
+  if (c->h_total) cudaFreeHost(c->h_total);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int32_t z2d_flush(z2d_ctx* c) {
+  if (!c) return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  return flush(c);
+}
+
+int32_t z2d_sync(z2d_ctx* c) {
+  if (!c) return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return Z2D_OK;
+}
+
+int32_t z2d_get_stats(const z2d_ctx* c, z2d_stats* out) {
+  if (!c || !out) return Z2D_E_INVALID_ARG;
+  *out = c->stats;
+  return Z2D_OK;
+}
+
+// ------------------------------------------------------------------------- surfaces
+int32_t z2d_surface_create(z2d_ctx* c, uint32_t format, int32_t width, int32_t height, const z2d_pixel* initial_px, z2d_sfc** out) {
+  if (!c || !out || format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
+  *out = nullptr;
+  if (width < 1) return Z2D_E_INVALID_WIDTH;    // surface.zig:389,628
+  if (height < 1) return Z2D_E_INVALID_HEIGHT;
+  cudaSetDevice(c->device);
+  z2d_sfc* s = new z2d_sfc();
+  s->ctx = c;
+  s->fmt = format;
+  s->w = width;
+  s->h = height;
+  s->bytes = ((size_t)width * (size_t)height * (size_t)fmt_bits(format) + 7) / 8;
+  s->batch_slot = -1;
+  const size_t alloc = (s->bytes + 31) & ~(size_t)15;  // word-granular atomics on packed formats may touch the padding
+  cudaError_t e = cudaMalloc((void**)&s->data, alloc);
+  if (e != cudaSuccess) {
+    delete s;
+    c->last_error = cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? Z2D_E_OUT_OF_MEMORY : Z2D_E_DEVICE;
+  }
+  e = cudaMemsetAsync(s->data, 0, alloc, c->stream);
+  if (e == cudaSuccess && initial_px) {
+    const uint32_t raw = pixel_to_raw(format, initial_px->format, initial_px->r, initial_px->g, initial_px->b, initial_px->a);
+    if (raw) launch_paint(s->data, format, (size_t)width * (size_t)height, raw, c->stream);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    cudaFree(s->data);
+    delete s;
+    return fail(c, "surface init", e);
+  }
+  *out = s;
+  return Z2D_OK;
+}
+
+void z2d_surface_destroy(z2d_sfc* s) {
+  if (!s) return;
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  if (s->batch_slot >= 0) flush(c);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(s->data);
+  delete s;
+}
+
+size_t z2d_surface_byte_len(const z2d_sfc* s) { return s ? s->bytes : 0; }
+int32_t z2d_surface_width(const z2d_sfc* s) { return s ? s->w : 0; }
+int32_t z2d_surface_height(const z2d_sfc* s) { return s ? s->h : 0; }
+uint32_t z2d_surface_format(const z2d_sfc* s) { return s ? s->fmt : 0; }
+void* z2d_surface_device_ptr(z2d_sfc* s) { return s ? s->data : nullptr; }
+
+int32_t z2d_surface_upload(z2d_sfc* s, const void* host, size_t n) {
+  if (!s || !host || n != s->bytes) return Z2D_E_INVALID_ARG;
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  CK(c, cudaMemcpyAsync(s->data, host, n, cudaMemcpyHostToDevice, c->stream));
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_download(z2d_sfc* s, void* host, size_t n) {
+  if (!s || !host || n != s->bytes) return Z2D_E_INVALID_ARG;
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  CK(c, cudaMemcpyAsync(host, s->data, n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_paint_pixel(z2d_sfc* s, const z2d_pixel* px) {
+  if (!s || !px || px->format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  const uint32_t raw = pixel_to_raw(s->fmt, px->format, px->r, px->g, px->b, px->a);
+  launch_paint(s->data, s->fmt, (size_t)s->w * (size_t)s->h, raw, c->stream);
+  CK(c, cudaGetLastError());
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_put_pixel(z2d_sfc* s, int32_t x, int32_t y, const z2d_pixel* px) {
+  if (!s || !px || px->format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
+  if (x < 0 || y < 0 || x >= s->w || y >= s->h) return Z2D_OK;  // surface.zig:520,770
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  const uint32_t raw = pixel_to_raw(s->fmt, px->format, px->r, px->g, px->b, px->a);
+  launch_put_pixel(s->data, s->fmt, (size_t)s->w * (size_t)y + (size_t)x, raw, c->stream);
+  CK(c, cudaGetLastError());
+  return Z2D_OK;
+}
+
+// ------------------------------------------------------------------------- painter
+static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_node* nodes, size_t n, DevDraw& d) {
+  const size_t save_g = c->grads.size(), save_o = c->stop_offsets.size(), save_c = c->stop_colors.size();
+  int rc = pattern_to_src(*pattern, d.src, c->grads, c->stop_offsets, c->stop_colors);
+  if (rc) return rc;
+  d.surface = batch_slot(c, s);
+  d.reduces = (d.src.kind == Z2D_PARAM_PIXEL && (d.op == Z2D_OP_SRC || (d.op == Z2D_OP_SRC_OVER && px_is_opaque(pattern->pixel)))) ? 1u : 0u;
+  d.paint_raw = d.src.kind == Z2D_PARAM_PIXEL
+                    ? pixel_to_raw(s->fmt, pattern->pixel.format, pattern->pixel.r, pattern->pixel.g, pattern->pixel.b, pattern->pixel.a)
+                    : 0u;
+  d.ext[0] = f64_order(INFINITY);
+  d.ext[1] = f64_order(-INFINITY);
+  d.ext[2] = f64_order(INFINITY);
+  d.ext[3] = f64_order(-INFINITY);
+  const size_t save_nodes = c->nodes.n, save_sp = c->subpaths.n;
+  const uint32_t di = (uint32_t)c->draws.n;
+  rc = record_nodes(c, di, nodes, n);
+  if (rc == Z2D_OK && !c->draws.push(d)) rc = Z2D_E_OUT_OF_MEMORY;
+  if (rc) {  // roll back: the failed call draws nothing
+    c->nodes.n = save_nodes;
+    c->subpaths.n = save_sp;
+    c->grads.resize(save_g);
+    c->stop_offsets.resize(save_o);
+    c->stop_colors.resize(save_c);
+    return rc;
+  }
+  if (c->nodes.n > kMaxBatchNodes || c->draws.n > kMaxBatchDraws) return flush(c);
+  return Z2D_OK;
+}
+
+int32_t z2d_fill(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_node* nodes, size_t n, const z2d_fill_opts* o) {
+  if (!c || !s || !pattern || !o || s->ctx != c || (n && !nodes)) return Z2D_E_INVALID_ARG;
+  if (o->op >= Z2D_OP_COUNT || o->fill_rule > 1 || o->precision > 1 || o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X) return Z2D_E_INVALID_ARG;
+  if (pattern->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(pattern->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;  // painter.zig:73-79
+  if (n == 0) return Z2D_OK;                                         // painter.zig:81
+  if (!is_closed_node_set(nodes, n)) return Z2D_E_PATH_NOT_CLOSED;   // painter.zig:82
+  cudaSetDevice(c->device);
+  DevDraw d;
+  memset(&d, 0, sizeof d);
+  d.kind = 0;
+  // painter.zig:88-97: 1-bit alpha surfaces are never anti-aliased; .default is MSAA
+  uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;
+  if (aa == Z2D_AA_DEFAULT) aa = Z2D_AA_MULTISAMPLE_4X;
+  d.aa = aa;
+  d.rule = o->fill_rule;
+  d.op = o->op;
+  d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;  // multisample.zig:36, compositor.zig:317-322
+  d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
+  d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;  // painter.zig:103
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {
+    c->last_error = "unbounded operator without anti-aliasing is not implemented on the device yet";
+    return Z2D_E_DEVICE;
+  }
+  return record_draw(c, s, pattern, nodes, n, d);
+}
+
+int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_node* nodes, size_t n, const z2d_stroke_opts* o) {
+  if (!c || !s || !pattern || !o || s->ctx != c || (n && !nodes)) return Z2D_E_INVALID_ARG;
+  if (pattern->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(pattern->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
+  {  // painter.zig:231: the CTM must be invertible (checked before the empty-node early-out)
+    const double ax = o->ctm[0], by = o->ctm[1], cx = o->ctm[2], dy = o->ctm[3];
+    if (by == 0 && cx == 0) {
+      if (ax == 0 || dy == 0) return Z2D_E_INVALID_MATRIX;
+    } else if (ax * dy - by * cx == 0) {
+      return Z2D_E_INVALID_MATRIX;
+    }
+  }
+  if (n == 0) return Z2D_OK;
+  c->last_error = "stroke is not implemented on the device yet";
+  return Z2D_E_DEVICE;
+}
+
+// ------------------------------------------------------------------------- compositor
+int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, const z2d_comp_op* ops, size_t n_ops, uint32_t precision) {
+  if (!c || !dst || dst->ctx != c || (n_ops && !ops) || precision > 1) return Z2D_E_INVALID_ARG;
+  if (n_ops > kMaxCompOps) return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = flush(c);  // ordering: everything recorded so far lands first
+  if (rc) return rc;
+  // compositor.zig:311-374
+  if (n_ops == 0) return Z2D_OK;
+  if (dst_x >= dst->w || dst_y >= dst->h) return Z2D_OK;
+  for (size_t k = 0; k < n_ops; k++) {
+    if (ops[k].op >= Z2D_OP_COUNT) return Z2D_E_INVALID_ARG;
+    if (op_requires_float(ops[k].op)) precision = Z2D_PRECISION_FLOAT;
+  }
+  int src_w, src_h;
+  switch (ops[0].src.kind) {
+    case Z2D_PARAM_NONE: return Z2D_OK;
+    case Z2D_PARAM_SURFACE: {
+      const z2d_sfc* ss = (const z2d_sfc*)ops[0].src.surface;
+      if (!ss) return Z2D_E_INVALID_ARG;
+      src_w = ss->w;
+      src_h = ss->h;
+      break;
+    }
+    default:
+      if (dst_x != 0 || dst_y != 0) return Z2D_OK;
+      src_w = dst->w;
+      src_h = dst->h;
+  }
+  const int src_start_x = dst_x < 0 ? -dst_x : 0, src_start_y = dst_y < 0 ? -dst_y : 0;
+  const int width = (src_w + dst_x > dst->w) ? dst->w - dst_x : src_w;
+  const int height = (src_h + dst_y > dst->h) ? dst->h - dst_y : src_h;
+  if (src_start_x >= width || src_start_y >= height) return Z2D_OK;
+
+  CompArgs A;
+  memset(&A, 0, sizeof A);
+  A.data = dst->data;
+  A.fmt = dst->fmt;
+  A.w = dst->w;
+  A.h = dst->h;
+  A.src_start_x = src_start_x;
+  A.src_start_y = src_start_y;
+  A.dst_start_x = src_start_x + dst_x;
+  A.dst_start_y = src_start_y + dst_y;
+  A.scan_w = width - src_start_x;
+  A.rows = height - src_start_y;
+  A.n_ops = (uint32_t)n_ops;
+  A.precision = precision;
+  std::vector<DevGrad> grads;
+  std::vector<float> offs;
+  std::vector<float4> cols;
+  auto conv = [&](const z2d_comp_param& p, DevSrc& s, uint32_t& has) -> int {
+    has = p.kind != Z2D_PARAM_NONE;
+    if (!has) return Z2D_OK;
+    if (p.kind == Z2D_PARAM_SURFACE) {
+      const z2d_sfc* ss = (const z2d_sfc*)p.surface;
+      if (!ss || ss->ctx != c) return Z2D_E_INVALID_ARG;
+      memset(&s, 0, sizeof s);
+      s.kind = Z2D_PARAM_SURFACE;
+      s.sdata = ss->data;
+      s.sfmt = ss->fmt;
+      s.sw = ss->w;
+      s.sh = ss->h;
+      return Z2D_OK;
+    }
+    return pattern_to_src(p.pattern, s, grads, offs, cols);
+  };
+  for (size_t k = 0; k < n_ops; k++) {
+    A.ops[k].op = ops[k].op;
+    if ((rc = conv(ops[k].dst, A.ops[k].dst, A.ops[k].has_dst))) return rc;
+    if ((rc = conv(ops[k].src, A.ops[k].src, A.ops[k].has_src))) return rc;
+  }
+  CK(c, upload(c, c->d_comp_grads, grads.data(), grads.size() * sizeof(DevGrad)));
+  CK(c, upload(c, c->d_comp_stop_off, offs.data(), offs.size() * 4));
+  CK(c, upload(c, c->d_comp_stop_col, cols.data(), cols.size() * sizeof(float4)));
+  A.T = tables(c, c->d_comp_grads, c->d_comp_stop_off, c->d_comp_stop_col);
+  launch_composite(A, c->sm_count, c->stream);
+  CK(c, cudaGetLastError());
+  c->stats.kernel_launches = 1;
+  return Z2D_OK;
+}
+
+}  // extern "C"
