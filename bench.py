@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""Benchmark of the fill -> coverage -> composite hot path (BASELINE.json config 2).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA library)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (rank 0 only)
+
+A *step* is one pass of the hot path over one batch: a zeroed 4096x4096 RGBA8
+canvas receives 100 000 ordered `painter.fill` calls (random closed 4-cubic
+paths, alternating non-zero / even-odd, translucent src_over, default AA).
+
+* `value`  : whole-job Mpix/s (pixels with coverage > 0, summed over paths) with the
+             batch already resident in HBM (z2d_replay), device-timed with CUDA events.
+* `e2e`    : same metric through the reference-facing C-ABI with HOST buffers:
+             z2d_submit of host node arrays (H2D inside), sync, D2H of the canvas.
+* `roofline`: the dominant kernel (k_raster_tiles): algorithmic bytes
+             (8 B per composited pixel + 32 B per binned edge) / its CUDA-event time.
+* `cpu_baseline`: the CPU restatement of z2d's path (oracle/, -O3 -march=native),
+             1 thread (the reference is single threaded), bounded sample.
+With N > 1 (torchrun) every rank renders its own independent scene (weak
+scaling, no data-path collective); times are max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filled+composited Mpix/s"
+UNIT = "Mpix/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_lib(fast=True):
+    from tests.oracle_backend import load_oracle
+    return load_oracle(fast=fast)
+
+
+def time_oracle(scene, n_sample, lib):
+    """Render the first n_sample draws of the scene with the CPU restatement; returns (seconds, covered_px)."""
+    from z2d_b200 import abi
+    buf = np.zeros(scene.width * scene.height * 4, dtype=np.uint8)
+    cmds = scene.draw_cmds(0, 0, n_sample)
+    lib.z2d_ref_covered_px(1)
+    P = C.POINTER
+    fill = lib.z2d_ref_fill
+    ptr = buf.ctypes.data_as(C.c_void_p)
+    pat = C.cast(C.c_void_p(int(cmds["pattern"][0])), P(abi.PatternPOD))
+    t0 = time.perf_counter()
+    for i in range(n_sample):
+        rc = fill(ptr, 3, scene.width, scene.height, C.cast(C.c_void_p(int(cmds["pattern"][i])), P(abi.PatternPOD)),
+                  C.cast(C.c_void_p(int(cmds["nodes"][i])), P(abi.Node)), int(cmds["n_nodes"][i]),
+                  C.cast(C.c_void_p(int(cmds["fill"][i])), P(abi.FillOptsPOD)))
+        assert rc == 0
+    dt = time.perf_counter() - t0
+    del pat
+    return dt, int(lib.z2d_ref_covered_px(1)), buf
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from z2d_b200 import workloads
+    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=0x7A326402)
+    lib = oracle_lib(fast=True)
+    n_sample = min(args.ref_sample, scene.n)
+    for _ in range(args.warmup):
+        time_oracle(scene, min(200, n_sample), lib)
+    tot_t, tot_px = 0.0, 0
+    for _ in range(args.steps):
+        dt, px, _ = time_oracle(scene, n_sample, lib)
+        tot_t += dt
+        tot_px += px
+    mpix = tot_px / tot_t / 1e6
+    paths_s = n_sample * args.steps / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "paths_per_s": paths_s,
+        "config": {"workload": f"BASELINE config 2: {args.size}x{args.size} RGBA8, {args.paths} random closed 4-cubic paths, "
+                               "non-zero/even-odd alternating, translucent src_over, default AA (MSAA 4x4), ordered",
+                   "sample": f"first {n_sample} draws of the scene per step"},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": paths_s,
+                         "sample": f"first {n_sample} of {scene.n} draws per step, x{args.steps} steps; C++ restatement of z2d's CPU path "
+                                   "(oracle/, g++ -O3 -march=native -ffp-contract=off), not z2d itself (no Zig toolchain); z2d is single threaded"},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from z2d_b200 import abi, workloads
+    from z2d_b200.cuda_backend import CudaBackend
+    from z2d_b200.host import Pixel, Surface
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    cb = CudaBackend(local_rank, stream=stream.cuda_stream)
+    lib = cb.lib
+
+    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=0x7A326402 + rank)
+    sfc = Surface(abi.Format.rgba, args.size, args.size, None, cb)
+    cmds = scene.draw_cmds(sfc.handle)
+    cmds_p = cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD))
+    zero = Pixel.rgba(0, 0, 0, 0)
+    nbytes = sfc.byte_len()
+    host_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_ptr = C.c_void_p(host_out.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_step():
+        sfc.paint_pixel(zero)
+        cb.submit(cmds_p, scene.n)
+        cb._check(lib.z2d_surface_download(sfc.handle, host_ptr, nbytes))  # flush + sync + D2H
+
+    def dev_step():
+        sfc.paint_pixel(zero)
+        cb.replay()
+
+    # ---- e2e (host buffers, H2D + D2H inside the timed region)
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    st = cb.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d_bytes = st["h2d_bytes"]
+
+    # ---- device-resident (value): replay of the uploaded batch, CUDA events on the launching stream
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    raster_ms, total_ms = [], []
+    ev0.record()
+    for _ in range(args.steps):
+        dev_step()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    # per-kernel time of the dominant kernel (CUDA events recorded inside the library on the same stream)
+    for _ in range(3):
+        dev_step()
+        s = cb.stats()
+        raster_ms.append(s["ms_raster"])
+        total_ms.append(s["ms_total"])
+    st = cb.stats()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(st["covered_px"]), float(st["draws"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    covered_all, draws_all = float(cnt[0]), float(cnt[1])
+
+    # ---- compositor kernel roofline (config 4 shape: 8192^2 RGBA8 src_over, single-pixel source)
+    comp = None
+    if rank == 0:
+        comp = composite_roofline(cb, args)
+
+    # ---- CPU baseline (rank 0, N == 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        olib = oracle_lib(fast=True)
+        n_sample = min(args.cpu_sample, scene.n)
+        dt, px, ref_buf = time_oracle(scene, n_sample, olib)
+        cpu = {"value": px / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": n_sample / dt,
+               "sample": f"first {n_sample} of {scene.n} draws, {dt:.1f} s; C++ restatement of z2d's CPU path (oracle/, -O3 -march=native), "
+                         f"1 thread (z2d is single threaded); host has {os.cpu_count()} cores"}
+        # parity spot check of the same sample on the device
+        chk = Surface(abi.Format.rgba, args.size, args.size, None, cb)
+        c2 = scene.draw_cmds(chk.handle, 0, n_sample)
+        cb.submit(c2.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), n_sample)
+        cpu["parity_sample_equal"] = bool(np.array_equal(chk.download(), ref_buf))
+        chk.deinit()
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        steps = args.steps
+        mpix = covered_all * steps / (dev_ms * 1e-3) / 1e6
+        e2e_mpix = covered_all * steps / (e2e_ms * 1e-3) / 1e6
+        r_ms = float(np.mean(raster_ms))
+        algo_bytes = 8.0 * st["covered_px"] + 32.0 * st["band_edges"]
+        achieved = algo_bytes / (r_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "paths_per_s": draws_all * steps / (dev_ms * 1e-3),
+            "config": {"workload": f"BASELINE config 2 per GPU: {args.size}x{args.size} RGBA8, {args.paths} random closed 4-cubic paths, "
+                                   "non-zero/even-odd alternating, translucent src_over, default AA (MSAA 4x4), ordered",
+                       "parallelism": f"independent scenes, 1 per GPU x{world} (no data-path collective)",
+                       "l2": "per-step inputs (nodes+draw table+edges+canvas ~ 340 MB) exceed the 126 MB L2; canvas cleared every step"},
+            "e2e": {"value": e2e_mpix, "unit": UNIT, "ms_per_step": e2e_ms / steps, "paths_per_s": draws_all * steps / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nbytes)},
+            "gpu_launches": int((st["kernel_launches"] + 1) * steps),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "ms": r_ms,
+                         "algorithmic_bytes": algo_bytes,
+                         "note": "algorithmic = 8 B per composited pixel (read+write RGBA8 per path, SURVEY 8d) + 32 B per binned edge; "
+                                 "the tile-resident design touches each canvas tile once per batch, so DRAM traffic is far below this"},
+            "stages_ms": {"flatten": st["ms_flatten"], "bin": st["ms_bin"], "lists": st["ms_lists"], "raster": r_ms,
+                          "pipeline_total": float(np.mean(total_ms))},
+            "counters": {k: int(st[k]) for k in ("draws", "nodes", "edges", "band_edges", "tile_items", "tiles", "covered_px", "region_px")},
+            "roofline_composite": comp,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def composite_roofline(cb, args):
+    """K5 on 8192^2 RGBA8, src_over with a translucent single-pixel source: 8 B/px algorithmic."""
+    import torch
+    from z2d_b200 import abi
+    from z2d_b200.host import Operation, Param, Pixel, Surface, SurfaceCompositor
+    n = 8192
+    sfc = Surface(abi.Format.rgba, n, n, Pixel.rgba(10, 20, 30, 200), cb)
+    ops = [Operation(abi.Operator.src_over, src=Param.pixel(Pixel.rgba(40, 30, 20, 128)))]
+    for _ in range(3):
+        SurfaceCompositor.run(sfc, 0, 0, ops)
+    reps = 10
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        SurfaceCompositor.run(sfc, 0, 0, ops)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    peak, kind = peaks()
+    achieved = 8.0 * n * n / (ms * 1e-3) / 1e9
+    sfc.deinit()
+    return {"kernel": "k_composite_v4", "workload": "8192x8192 RGBA8 src_over, single-pixel source (BASELINE config 4 shape)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "ms": ms,
+            "mpix_per_s": n * n / (ms * 1e-3) / 1e6, "peak_kind": kind}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=100_000)
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--ref-sample", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        import __graft_entry__  # make sure the library exists (no-op when already built)
+        from z2d_b200 import build as zbuild
+        zbuild.build()
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -229,13 +229,42 @@ int32_t z2d_stroke(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,
 int32_t z2d_composite(z2d_ctx* ctx, z2d_sfc* dst, int32_t dst_x, int32_t dst_y,
                       const z2d_comp_op* ops, size_t n_ops, uint32_t precision);
 
-/* Statistics of the last flushed batch (counters the benchmark reports). */
+/* Batched, ordered submission: equivalent to calling z2d_fill / z2d_stroke once
+ * per element, in order (the loop a caller of painter.fill/stroke would run;
+ * BASELINE configs 2, 3 and 5 issue 10^5 calls).  statuses may be NULL; the
+ * return value is the first non-OK status (later commands are still recorded). */
+typedef struct z2d_draw_cmd {
+  uint32_t kind;                 /* 0 = fill, 1 = stroke */
+  uint32_t _pad;
+  z2d_sfc* surface;
+  const z2d_pattern* pattern;
+  const z2d_node* nodes;
+  size_t n_nodes;
+  const z2d_fill_opts* fill;     /* kind 0 */
+  const z2d_stroke_opts* stroke; /* kind 1 */
+} z2d_draw_cmd;
+int32_t z2d_submit(z2d_ctx* ctx, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses);
+
+/* Re-executes the device pipeline of the most recently flushed batch from its
+ * device-resident inputs (nodes, draw table); nothing is read from the host.
+ * Benchmarking aid: separates kernel time from host recording and H2D copies. */
+int32_t z2d_replay(z2d_ctx* ctx);
+
+/* Statistics of the last executed batch (counters and device timings the
+ * benchmark reports; times are CUDA-event milliseconds on the context stream). */
 typedef struct z2d_stats {
-  uint64_t draws;        /* fill/stroke calls executed */
-  uint64_t edges;        /* flattened polygon edges */
-  uint64_t tile_items;   /* (draw, tile) pairs rasterised */
-  uint64_t crossings;    /* edge x sub-scanline evaluations (upper bound) */
+  uint64_t draws;         /* fill/stroke calls executed */
+  uint64_t nodes;         /* path nodes uploaded */
+  uint64_t edges;         /* flattened polygon edges (32 B each) */
+  uint64_t band_edges;    /* edge references after tile-row binning */
+  uint64_t tile_items;    /* entries of the per-tile-row ordered draw lists */
+  uint64_t tiles;         /* tiles the raster kernel was launched over */
+  uint64_t covered_px;    /* sum over draws of pixels with coverage > 0 (composited pixels) */
+  uint64_t region_px;     /* sum over draws of the evaluated bounding-region pixels */
   uint64_t kernel_launches;
+  uint64_t h2d_bytes;     /* bytes uploaded for the batch */
+  float ms_flatten, ms_bin, ms_lists, ms_raster, ms_total;
+  float _pad;
 } z2d_stats;
 int32_t z2d_get_stats(const z2d_ctx* ctx, z2d_stats* out);
 

@@ -36,6 +36,13 @@ int32_t z2d_ref_surface_put_pixel(void* buf, uint32_t fmt, int32_t w, int32_t h,
   return Z2D_OK;
 }
 
+// benchmark statistic: pixels with coverage > 0 composited so far by the MSAA rasteriser
+uint64_t z2d_ref_covered_px(int32_t reset) {
+  uint64_t v = g_covered_px;
+  if (reset) g_covered_px = 0;
+  return v;
+}
+
 static int check_pattern(const z2d_pattern* p) {  // painter.zig:73-79
   if (p->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(p->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
   return Z2D_OK;

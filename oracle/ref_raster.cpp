@@ -8,6 +8,8 @@
 
 namespace zref {
 
+uint64_t g_covered_px = 0;  // pixels with coverage > 0 composited by the MSAA rasteriser (benchmark statistic)
+
 // ----------------------------------------------------------------- Polygon
 void Polygon::add_edge(Pt p0, Pt p1) {  // Polygon.zig:61-109
   Pt a{p0.x * scale, p0.y * scale}, b{p1.x * scale, p1.y * scale};
@@ -318,6 +320,7 @@ void raster_multisample(Sfc& s, const Src& pat, Polygon& poly, uint32_t rule, ui
       int c = std::min<int>(cov[(size_t)cx], cov_full);
       if (x >= W) break;
       if (c == 0) continue;
+      g_covered_px++;
       if (c == cov_full)
         composite_opaque(op, s, pat, x, y, 1, prec);
       else

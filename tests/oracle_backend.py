@@ -37,6 +37,8 @@ def load_oracle(fast=False):
     lib.z2d_ref_surface_paint_pixel.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, P(abi.PixelPOD)]
     lib.z2d_ref_surface_put_pixel.restype = C.c_int32
     lib.z2d_ref_surface_put_pixel.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(abi.PixelPOD)]
+    lib.z2d_ref_covered_px.restype = C.c_uint64
+    lib.z2d_ref_covered_px.argtypes = [C.c_int32]
     lib.z2d_ref_fill.restype = C.c_int32
     lib.z2d_ref_fill.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]
     lib.z2d_ref_stroke.restype = C.c_int32

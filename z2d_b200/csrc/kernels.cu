@@ -269,8 +269,20 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
 // =====================================================================================
 Z2D_D int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
 
+__global__ void k_reset_draws(DevDraw* __restrict__ draws, uint32_t n_draws) {  // replay: undo what the pipeline wrote
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_draws) return;
+  DevDraw& d = draws[i];
+  d.ext[0] = f64_order(INFINITY);
+  d.ext[1] = f64_order(-INFINITY);
+  d.ext[2] = f64_order(INFINITY);
+  d.ext[3] = f64_order(-INFINITY);
+  d.n_edges = 0;
+  d.valid = 0;
+}
+
 __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
-                              uint32_t* __restrict__ draw_bands) {
+                              uint32_t* __restrict__ draw_bands, unsigned long long* __restrict__ counters) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
   DevDraw& d = draws[i];
@@ -327,6 +339,7 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
   }
   d.valid = 1;
   draw_bands[i] = (uint32_t)(d.ey1 - d.ey0 + 1);
+  if (counters) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
 }
 
 __global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off) {
@@ -614,6 +627,7 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
   const int py = ty * kTile + row;
   const int px0 = tx * kTile + half * 8;
   bool loaded = false, dirty = false;
+  uint32_t n_cov = 0;
   const size_t row_idx = (size_t)py * (size_t)S.w;
 
   for (uint32_t base = lb; base < le; base += 32) {
@@ -683,6 +697,7 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
         }
         if (x >= d.rx0 && x < d.rx1 && py >= d.ry0 && py < d.ry1) {
           const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
+          n_cov += cov > 0;
           raw = composite_cov(d, A.T, S.fmt, raw, cov, x, py);
         }
         px[i * 32 + lane] = raw;
@@ -695,6 +710,10 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
       const int x = px0 + i;
       if (x < S.w && py < S.h) store_raw(S.data, S.fmt, row_idx + (size_t)x, px[i * 32 + lane]);
     }
+  }
+  if (A.counters) {
+    n_cov = __reduce_add_sync(0xffffffffu, n_cov);
+    if (lane == 0 && n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
   }
 }
 
@@ -780,8 +799,11 @@ void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
                          DevEdge* edges, uint32_t* edge_draw, cudaStream_t st) {
   if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw);
 }
-void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, cudaStream_t st) {
-  if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands);
+void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, unsigned long long* counters, cudaStream_t st) {
+  if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, counters);
+}
+void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st) {
+  if (n) k_reset_draws<<<blocks_for(n, 256), 256, 0, st>>>(draws, n);
 }
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, cudaStream_t st) {
   if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off);

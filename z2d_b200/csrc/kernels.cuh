@@ -18,6 +18,7 @@ struct RasterArgs {
   const DevDraw* draws;
   const uint32_t* band_off;    // per (draw, tile-row) slot (+1): offset into band_edges
   const DevEdge* band_edges;
+  unsigned long long* counters;  // [0] covered pixels, [1] region pixels (may be null)
   GradTables T;
 };
 
@@ -44,7 +45,8 @@ void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, cudaStream_t st);
-void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, cudaStream_t st);
+void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, unsigned long long* counters, cudaStream_t st);
+void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st);
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, cudaStream_t st);
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,

@@ -84,6 +84,12 @@ struct z2d_sfc {
   int32_t batch_slot;  // index in the current batch's surface table, or -1
 };
 
+struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
+  bool valid = false;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0;
+  size_t n_nodes = 0, h2d_bytes = 0;
+};
+
 struct z2d_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -107,6 +113,10 @@ struct z2d_ctx {
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
   DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
   uint32_t* h_total = nullptr;  // pinned readback slot
+  DevBuf d_counters;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  BatchMeta last;
+  bool stats_pending = false;
 };
 
 namespace {
@@ -315,6 +325,118 @@ GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& s
 }
 
 // ------------------------------------------------------------------ the pipeline
+// The device stage of a batch: everything it reads is device resident (replayable).
+int run_pipeline(z2d_ctx* c, bool replay) {
+  const BatchMeta& m = c->last;
+  if (!m.valid || m.n_draws == 0) return Z2D_OK;
+  cudaStream_t st = c->stream;
+  const uint32_t n_draws = m.n_draws, n_sp = m.n_sp, n_sfc = m.n_sfc, n_work = m.n_work;
+  uint32_t launches = 0;
+  auto scan = [&](DevBuf& in, DevBuf& out, uint32_t n) -> cudaError_t {
+    cudaError_t e = out.ensure(((size_t)n + 1) * 4);
+    if (e != cudaSuccess) return e;
+    e = c->d_scan_tmp.ensure(scan_tmp_len(n) * 4);
+    if (e != cudaSuccess) return e;
+    exclusive_scan(in.as<uint32_t>(), out.as<uint32_t>(), n, c->d_scan_tmp.as<uint32_t>(), st);
+    launches += 3;
+    return cudaGetLastError();
+  };
+  CK(c, c->d_counters.ensure(64));
+  CK(c, cudaMemsetAsync(c->d_counters.p, 0, 64, st));
+  if (replay) launch_reset_draws(c->d_draws.as<DevDraw>(), n_draws, st);
+  CK(c, cudaEventRecord(c->ev[0], st));
+
+  // K1: flatten (count, scan, emit)
+  CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
+  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(), st);
+  CK(c, scan(c->d_sp_count, c->d_sp_off, n_sp));
+  uint32_t n_edges = 0;
+  {
+    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
+    if (rc) return rc;
+  }
+  CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
+  CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
+  launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
+                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), st);
+  CK(c, cudaEventRecord(c->ev[1], st));
+
+  // K2: per-draw regions; (draw, tile-row) slots
+  CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
+  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(),
+                     c->d_counters.as<unsigned long long>(), st);
+  CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
+  uint32_t n_slots = 0;
+  {
+    int rc = read_total(c, c->d_draw_band_off.as<uint32_t>() + n_draws, n_slots);
+    if (rc) return rc;
+  }
+  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), st);
+
+  // K3a: edges -> (draw, tile-row) lists
+  CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
+  CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
+  CK(c, cudaMemsetAsync(c->d_band_count.p, 0, (size_t)n_slots * 4 + 16, st));
+  CK(c, cudaMemsetAsync(c->d_band_cursor.p, 0, (size_t)n_slots * 4 + 16, st));
+  launch_bin_count(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_count.as<uint32_t>(), st);
+  CK(c, scan(c->d_band_count, c->d_band_off, n_slots));
+  uint32_t n_band_edges = 0;
+  {
+    int rc = read_total(c, c->d_band_off.as<uint32_t>() + n_slots, n_band_edges);
+    if (rc) return rc;
+  }
+  CK(c, c->d_band_edges.ensure((size_t)n_band_edges * sizeof(DevEdge) + 32));
+  launch_bin_scatter(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_off.as<uint32_t>(),
+                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), st);
+  CK(c, cudaEventRecord(c->ev[2], st));
+
+  // K3b: ordered draw list per surface tile-row
+  CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
+  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(),
+                    c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
+  CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
+  uint32_t n_items = 0;
+  {
+    int rc = read_total(c, c->d_list_off.as<uint32_t>() + n_work, n_items);
+    if (rc) return rc;
+  }
+  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
+  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(), nullptr,
+                    c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
+  CK(c, cudaEventRecord(c->ev[3], st));
+
+  // K4: fused coverage + compositing
+  RasterArgs A;
+  A.sfcs = c->d_sfcs.as<DevSurface>();
+  A.n_sfc = n_sfc;
+  A.n_tiles = m.n_tiles;
+  A.work_base = c->d_work_base.as<uint32_t>();
+  A.list_off = c->d_list_off.as<uint32_t>();
+  A.list_items = c->d_list_items.as<uint2>();
+  A.draws = c->d_draws.as<DevDraw>();
+  A.band_off = c->d_band_off.as<uint32_t>();
+  A.band_edges = c->d_band_edges.as<DevEdge>();
+  A.counters = c->d_counters.as<unsigned long long>();
+  A.T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
+  launch_raster(A, st);
+  CK(c, cudaGetLastError());
+  CK(c, cudaEventRecord(c->ev[4], st));
+  launches += 8 + (replay ? 1 : 0);
+
+  z2d_stats& s = c->stats;
+  memset(&s, 0, sizeof s);
+  s.draws = n_draws;
+  s.nodes = m.n_nodes;
+  s.edges = n_edges;
+  s.band_edges = n_band_edges;
+  s.tile_items = n_items;
+  s.tiles = m.n_tiles;
+  s.kernel_launches = launches;
+  s.h2d_bytes = replay ? 0 : m.h2d_bytes;
+  c->stats_pending = true;
+  return Z2D_OK;
+}
+
 int flush_impl(z2d_ctx* c) {
   const uint32_t n_draws = (uint32_t)c->draws.n;
   if (n_draws == 0) {
@@ -373,96 +495,20 @@ int flush_impl(z2d_ctx* c) {
   CK(c, upload(c, c->d_grads, c->grads.data(), c->grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_stop_off, c->stop_offsets.data(), c->stop_offsets.size() * 4));
   CK(c, upload(c, c->d_stop_col, c->stop_colors.data(), c->stop_colors.size() * sizeof(float4)));
-
-  uint32_t launches = 0;
-  auto scan = [&](DevBuf& in, DevBuf& out, uint32_t n) -> cudaError_t {
-    cudaError_t e = out.ensure(((size_t)n + 1) * 4);
-    if (e != cudaSuccess) return e;
-    e = c->d_scan_tmp.ensure(scan_tmp_len(n) * 4);
-    if (e != cudaSuccess) return e;
-    exclusive_scan(in.as<uint32_t>(), out.as<uint32_t>(), n, c->d_scan_tmp.as<uint32_t>(), st);
-    launches += 3;
-    return cudaGetLastError();
-  };
-
-  // 3. K1: flatten (count, scan, emit)
-  CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
-  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(), st);
-  CK(c, scan(c->d_sp_count, c->d_sp_off, n_sp));
-  uint32_t n_edges = 0;
-  {
-    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
-    if (rc) return rc;
-  }
-  CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
-  CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
-  launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), st);
-
-  // 4. K2: per-draw regions; (draw, tile-row) slots
-  CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
-  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(), st);
-  CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
-  uint32_t n_slots = 0;
-  {
-    int rc = read_total(c, c->d_draw_band_off.as<uint32_t>() + n_draws, n_slots);
-    if (rc) return rc;
-  }
-  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), st);
-
-  // 5. K3a: edges -> (draw, tile-row) lists
-  CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
-  CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
-  CK(c, cudaMemsetAsync(c->d_band_count.p, 0, (size_t)n_slots * 4 + 16, st));
-  CK(c, cudaMemsetAsync(c->d_band_cursor.p, 0, (size_t)n_slots * 4 + 16, st));
-  launch_bin_count(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_count.as<uint32_t>(), st);
-  CK(c, scan(c->d_band_count, c->d_band_off, n_slots));
-  uint32_t n_band_edges = 0;
-  {
-    int rc = read_total(c, c->d_band_off.as<uint32_t>() + n_slots, n_band_edges);
-    if (rc) return rc;
-  }
-  CK(c, c->d_band_edges.ensure((size_t)n_band_edges * sizeof(DevEdge) + 32));
-  launch_bin_scatter(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_off.as<uint32_t>(),
-                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), st);
-
-  // 6. K3b: ordered draw list per surface tile-row
-  CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
-  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(),
-                    c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
-  CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
-  uint32_t n_items = 0;
-  {
-    int rc = read_total(c, c->d_list_off.as<uint32_t>() + n_work, n_items);
-    if (rc) return rc;
-  }
-  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
-  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(), nullptr,
-                    c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
-
-  // 7. K4: fused coverage + compositing
-  RasterArgs A;
-  A.sfcs = c->d_sfcs.as<DevSurface>();
-  A.n_sfc = n_sfc;
-  A.n_tiles = n_tiles;
-  A.work_base = c->d_work_base.as<uint32_t>();
-  A.list_off = c->d_list_off.as<uint32_t>();
-  A.list_items = c->d_list_items.as<uint2>();
-  A.draws = c->d_draws.as<DevDraw>();
-  A.band_off = c->d_band_off.as<uint32_t>();
-  A.band_edges = c->d_band_edges.as<DevEdge>();
-  A.T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
-  launch_raster(A, st);
-  CK(c, cudaGetLastError());
-  launches += 8;
-
-  c->stats.draws = n_draws;
-  c->stats.edges = n_edges;
-  c->stats.tile_items = n_items;
-  c->stats.crossings = n_band_edges;
-  c->stats.kernel_launches = launches;
+  BatchMeta& m = c->last;
+  m.valid = true;
+  m.n_draws = n_draws;
+  m.n_sp = n_sp;
+  m.n_sfc = n_sfc;
+  m.n_tiles = n_tiles;
+  m.n_work = n_work;
+  m.n_nodes = c->nodes.n;
+  m.h2d_bytes = c->nodes.n * sizeof(z2d_node) + c->subpaths.n * sizeof(DevSubPath) + c->draws.n * sizeof(DevDraw) +
+                sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + c->grads.size() * sizeof(DevGrad) +
+                c->stop_offsets.size() * 4 + c->stop_colors.size() * sizeof(float4);
+  int rc = run_pipeline(c, false);
   clear_batch(c);
-  return Z2D_OK;
+  return rc;
 }
 
 int flush(z2d_ctx* c) {
@@ -554,6 +600,7 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
     c->own_stream = true;
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (auto& e : c->ev) cudaEventCreate(&e);
   if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
       cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
     delete c;
@@ -577,6 +624,8 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   c->subpaths.release();
   c->draws.release();
   if (c->h_total) cudaFreeHost(c->h_total);
+  c->d_counters.release();
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -596,10 +645,33 @@ int32_t z2d_sync(z2d_ctx* c) {
   return Z2D_OK;
 }
 
-int32_t z2d_get_stats(const z2d_ctx* c, z2d_stats* out) {
-  if (!c || !out) return Z2D_E_INVALID_ARG;
+int32_t z2d_get_stats(const z2d_ctx* cc, z2d_stats* out) {
+  if (!cc || !out) return Z2D_E_INVALID_ARG;
+  z2d_ctx* c = const_cast<z2d_ctx*>(cc);
+  if (c->stats_pending) {  // device counters and stage timings of the last batch
+    cudaSetDevice(c->device);
+    CK(c, cudaStreamSynchronize(c->stream));
+    unsigned long long h[2] = {0, 0};
+    CK(c, cudaMemcpy(h, c->d_counters.p, 16, cudaMemcpyDeviceToHost));
+    c->stats.covered_px = h[0];
+    c->stats.region_px = h[1];
+    cudaEventElapsedTime(&c->stats.ms_flatten, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->stats.ms_bin, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->stats.ms_lists, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->stats.ms_raster, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&c->stats.ms_total, c->ev[0], c->ev[4]);
+    c->stats_pending = false;
+  }
   *out = c->stats;
   return Z2D_OK;
+}
+
+int32_t z2d_replay(z2d_ctx* c) {
+  if (!c) return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  return run_pipeline(c, true);
 }
 
 // ------------------------------------------------------------------------- surfaces
@@ -772,6 +844,19 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   return Z2D_E_DEVICE;
 }
 
+int32_t z2d_submit(z2d_ctx* c, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses) {
+  if (!c || (n && !cmds)) return Z2D_E_INVALID_ARG;
+  int32_t first = Z2D_OK;
+  for (size_t i = 0; i < n; i++) {
+    const z2d_draw_cmd& k = cmds[i];
+    int32_t rc = k.kind == 0 ? z2d_fill(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.fill)
+                             : z2d_stroke(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.stroke);
+    if (statuses) statuses[i] = rc;
+    if (rc != Z2D_OK && first == Z2D_OK) first = rc;
+  }
+  return first;
+}
+
 // ------------------------------------------------------------------------- compositor
 int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, const z2d_comp_op* ops, size_t n_ops, uint32_t precision) {
   if (!c || !dst || dst->ctx != c || (n_ops && !ops) || precision > 1) return Z2D_E_INVALID_ARG;
@@ -851,6 +936,7 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   launch_composite(A, c->sm_count, c->stream);
   CK(c, cudaGetLastError());
   c->stats.kernel_launches = 1;
+  c->stats_pending = false;
   return Z2D_OK;
 }
 

@@ -51,6 +51,8 @@ def load_library():
         "z2d_fill": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]),
         "z2d_stroke": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.StrokeOptsPOD)]),
         "z2d_composite": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, P(abi.CompOpPOD), C.c_size_t, C.c_uint32]),
+        "z2d_submit": (C.c_int32, [vp, P(abi.DrawCmdPOD), C.c_size_t, P(C.c_int32)]),
+        "z2d_replay": (C.c_int32, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -64,7 +66,7 @@ EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
                     "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_paint_pixel",
-                    "z2d_surface_put_pixel", "z2d_fill", "z2d_stroke", "z2d_composite"]
+                    "z2d_surface_put_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
 
 
 class CudaBackend:
@@ -141,6 +143,13 @@ class CudaBackend:
             raise abi.DeviceError(self.lib.z2d_last_error(self.ctx).decode())
         return rc
 
+    def submit(self, cmds, n):
+        """z2d_submit: `cmds` is a ctypes array of abi.DrawCmdPOD."""
+        self._check(self.lib.z2d_submit(self.ctx, cmds, n, None))
+
+    def replay(self):
+        self._check(self.lib.z2d_replay(self.ctx))
+
     def flush(self):
         self._check(self.lib.z2d_flush(self.ctx))
 
@@ -150,4 +159,4 @@ class CudaBackend:
     def stats(self):
         s = abi.StatsPOD()
         self._check(self.lib.z2d_get_stats(self.ctx, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in abi.StatsPOD._fields_}
+        return {k: getattr(s, k) for k, _ in abi.StatsPOD._fields_ if not k.startswith("_")}
