@@ -282,13 +282,14 @@ __global__ void k_reset_draws(DevDraw* __restrict__ draws, uint32_t n_draws) {  
 }
 
 __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
-                              uint32_t* __restrict__ draw_bands, unsigned long long* __restrict__ counters) {
+                              uint32_t* __restrict__ draw_bands, DrawBox* __restrict__ boxes, unsigned long long* __restrict__ counters) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
   DevDraw& d = draws[i];
   const DevSurface s = sfcs[d.surface];
   d.valid = 0;
   draw_bands[i] = 0;
+  boxes[i] = DrawBox{-1, -1, -1, -1};
   if (d.n_edges == 0) return;
   const double top = f64_unorder(d.ext[0]), bottom = f64_unorder(d.ext[1]);
   const double left = f64_unorder(d.ext[2]), right = f64_unorder(d.ext[3]);
@@ -338,13 +339,26 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
     d.ty0 = d.ey0; d.ty1 = d.ey1;
   }
   d.valid = 1;
+  boxes[i] = DrawBox{d.tx0, d.tx1, d.ty0, d.ty1};
   draw_bands[i] = (uint32_t)(d.ey1 - d.ey0 + 1);
   if (counters) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
 }
 
-__global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off) {
+// second half of the setup: (draw, tile-row) slot base + the compact record the raster kernel reads
+__global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off,
+                                   DrawHot* __restrict__ hots) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_draws) draws[i].band_base = band_off[i];
+  if (i >= n_draws) return;
+  DevDraw& d = draws[i];
+  d.band_base = band_off[i];
+  DrawHot h;
+  h.aa = d.aa; h.rule = d.rule; h.op = d.op; h.precision = d.precision;
+  h.reduces = d.reduces; h.paint_raw = d.paint_raw; h.px_rgba = d.src.px_rgba; h.src_kind = d.src.kind;
+  h.rx0 = d.rx0; h.rx1 = d.rx1; h.ry0 = d.ry0; h.ry1 = d.ry1;
+  h.ey0 = d.ey0; h.ey1 = d.ey1;
+  h.band_base = d.band_base; h.unbounded = d.unbounded;
+  h.pre_y0 = d.pre_y0; h.pre_y1 = d.pre_y1; h.pre_x = d.pre_x; h.pre_rows = d.pre_rows;
+  hots[i] = h;
 }
 
 // =====================================================================================
@@ -410,7 +424,7 @@ Z2D_D uint32_t find_surface_by(const DevSurface* sfcs, uint32_t n_sfc, const uin
 
 template <bool WRITE>
 __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
-                             uint32_t n_work, const DevDraw* __restrict__ draws, uint32_t* __restrict__ cnt,
+                             uint32_t n_work, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
                              const uint32_t* __restrict__ off, uint2* __restrict__ items) {
   uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_work) return;
@@ -426,296 +440,22 @@ __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc
   uint32_t n = 0;
   uint32_t o = WRITE ? off[w] : 0u;
   for (uint32_t i = b; i < e; i++) {
-    const DevDraw& d = draws[i];
-    if (d.valid && band >= d.ty0 && band <= d.ty1) {
+    const DrawBox d = boxes[i];
+    if (d.tx0 >= 0 && band >= d.ty0 && band <= d.ty1) {
       if (WRITE) items[o + n] = make_uint2(i, (uint32_t)d.tx0 | ((uint32_t)d.tx1 << 16));
       n++;
     }
   }
   if (!WRITE) cnt[w] = n;
 }
-template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DevDraw*, uint32_t*,
+template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DrawBox*, uint32_t*,
                                              const uint32_t*, uint2*);
-template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DevDraw*, uint32_t*,
+template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DrawBox*, uint32_t*,
                                             const uint32_t*, uint2*);
 
-// =====================================================================================
-// per-pixel compositing for a rasterised draw (raster/shared.zig, multisample.zig:195-227,
-// supersample.zig:159-184, direct.zig:88-124)
-// =====================================================================================
-Z2D_D RGBA16 mask_mul16(RGBA16 s, int m) { return {iM(s.r, m), iM(s.g, m), iM(s.b, m), iM(s.a, m)}; }  // dst_in(dst:=s, src:=alpha8 m)
-
-// generic StrideCompositor batch: [dst_in(pattern, mask)]? ; op        (shared.zig:24-45, 78-102)
-__device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables& T, uint32_t fmt, uint32_t raw, int mask8,
-                                                   bool use_mask, int x, int y) {
-  if (d.precision == Z2D_PRECISION_INTEGER) {
-    RGBA16 s = src_int(d.src, T, x, y, 0);
-    if (use_mask) s = mask_mul16(s, mask8);
-    return rgba16_to_raw(fmt, int_op(d.op, raw_to_rgba16(fmt, raw), s));
-  }
-  RGBAF s = src_float(d.src, T, x, y, 0);
-  if (use_mask) {
-    const float ma = (float)mask8 / 255.0f;
-    s = {s.r * ma, s.g * ma, s.b * ma, ma * s.a};
-  }
-  RGBAF r = float_op(d.op, decode_raw(raw_to_rgba16(fmt, raw)), s);
-  return rgba16_to_raw(fmt, encode_raw(r));
-}
-
-// cov: number of covered samples (MSAA/SSAA: 0..16, none: 0..1).  Returns the new raw pixel.
-Z2D_D uint32_t composite_cov(const DevDraw& d, const GradTables& T, uint32_t fmt, uint32_t raw, int cov, int x, int y) {
-  if (d.aa == Z2D_AA_SUPERSAMPLE_4X) {
-    // mask = box average of 16 samples in the mask surface's own format (supersample.zig:82-91, pixel.zig:435-464,633-646)
-    int m8;
-    if (fmt == Z2D_FMT_ALPHA4 || fmt == Z2D_FMT_ALPHA2 || fmt == Z2D_FMT_ALPHA1) {
-      const int bits = fmt_bits(fmt);
-      m8 = scale_alpha((((1 << bits) - 1) * cov) / 16, bits, 8);
-    } else {
-      m8 = (255 * cov) / 16;
-    }
-    return composite_generic(d, T, fmt, raw, m8, true, x, y);
-  }
-  if (cov == 0) return raw;
-  if (d.op == Z2D_OP_CLEAR) return 0u;  // shared.zig:18,60 (also at partial coverage)
-  const bool full = (d.aa == Z2D_AA_NONE) || cov == 16;
-  if (full) {
-    if (d.reduces) return d.paint_raw;
-    return composite_generic(d, T, fmt, raw, 255, false, x, y);
-  }
-  const int o = 16 * cov - 1;  // multisample.zig:223
-  if (d.reduces) {             // surface.zig:557-581 compositeStride (integer only)
-    RGBA16 s = mask_mul16(unpack_rgba(d.src.px_rgba), o);
-    return rgba16_to_raw(fmt, int_op(d.op, raw_to_rgba16(fmt, raw), s));
-  }
-  return composite_generic(d, T, fmt, raw, o, true, x, y);
-}
-
-// =====================================================================================
-// K4: fused coverage + compositing, one warp per 16x16-pixel tile
-// =====================================================================================
-template <int W>
-Z2D_D void wind_add(uint64_t (&p)[W], uint64_t mask, int dir) {
-  uint64_t c = mask;
-  if (dir > 0) {
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-      const uint64_t t = p[k] & c;
-      p[k] ^= c;
-      c = t;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-      const uint64_t t = ~p[k] & c;
-      p[k] ^= c;
-      c = t;
-    }
-  }
-}
-
-// Accumulate the inside-masks of this lane's sub-scanlines for one draw in one tile.
-// Sample column s (device sample units) is inside iff the signed count of active edges
-// with x_i <= s is non-zero (non_zero) / odd (even_odd)  -- Polygon.zig:302-353.
-Z2D_D double4 ld_edge(const DevEdge* e) {  // 2 x 128-bit read-only loads
-  const double2* q = reinterpret_cast<const double2*>(e);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
-
-// Column (relative to the tile's first sample) at which edge `ev` crosses sub-scanline
-// centre ym, or -1 when the edge is inactive there / crosses right of the tile.
-Z2D_D int edge_col(const double4& ev, double top, double bottom, double ym, int sx0, int ncols) {
-  if (!(top < ym && ym <= bottom)) return -1;
-  const double xf = round_half_away(ev.z + (ev.w * (ym - top)));  // Polygon.zig:305
-  const double cf = xf - (double)sx0;
-  if (!(cf < (double)ncols)) return -1;
-  return cf < 0.0 ? 0 : (int)cf;
-}
-
-// Inside-mask of ONE sub-scanline of a tile, bit-sliced winding in W registers (|winding| < 2^(W-1)).
-template <int W>
-Z2D_D uint64_t row_mask(const DevEdge* __restrict__ be, uint32_t n_be, int ys, int sx0, int ncols, uint32_t rule) {
-  uint64_t p[W];
-#pragma unroll
-  for (int k = 0; k < W; k++) p[k] = 0ull;
-  const double ym = (double)ys + 0.5;
-  const double xlim = (double)(sx0 + ncols) + 1.0;
-  for (uint32_t i = 0; i < n_be; i++) {
-    const double4 ev = ld_edge(be + i);  // y0,y1,x_start,x_inc (warp-uniform address)
-    const bool down = ev.x < ev.y;
-    const double top = down ? ev.x : ev.y, bottom = down ? ev.y : ev.x;
-    // warp-uniform cull: an edge entirely to the right of the tile contributes nothing
-    const double xe = ev.z + ev.w * (bottom - top);
-    if ((ev.z < xe ? ev.z : xe) > xlim) continue;
-    const int col = edge_col(ev, top, bottom, ym, sx0, ncols);
-    if (col >= 0) {
-      const uint64_t mask = ~0ull << col;
-      if (rule == Z2D_FILL_EVEN_ODD) p[0] ^= mask; else wind_add<W>(p, mask, down ? -1 : 1);
-    }
-  }
-  if (rule == Z2D_FILL_EVEN_ODD) return p[0];
-  uint64_t a = 0;
-#pragma unroll
-  for (int k = 0; k < W; k++) a |= p[k];
-  return a;
-}
-
-// Same, for tile-rows holding so many edges of one draw that the winding number could
-// exceed the register-resident counter: 32 bit-planes in local memory (rare).
-__device__ __noinline__ uint64_t row_mask_wide(const DevEdge* __restrict__ be, uint32_t n_be, int ys, int sx0, int ncols, uint32_t rule) {
-  uint64_t p[32];
-  for (int k = 0; k < 32; k++) p[k] = 0ull;
-  const double ym = (double)ys + 0.5;
-  for (uint32_t i = 0; i < n_be; i++) {
-    const double4 ev = ld_edge(be + i);
-    const bool down = ev.x < ev.y;
-    const double top = down ? ev.x : ev.y, bottom = down ? ev.y : ev.x;
-    const int col = edge_col(ev, top, bottom, ym, sx0, ncols);
-    if (col < 0) continue;
-    uint64_t c = ~0ull << col;
-    if (rule == Z2D_FILL_EVEN_ODD) {
-      p[0] ^= c;
-    } else if (!down) {
-      for (int k = 0; k < 32 && c; k++) { const uint64_t t = p[k] & c; p[k] ^= c; c = t; }
-    } else {
-      for (int k = 0; k < 32 && c; k++) { const uint64_t t = ~p[k] & c; p[k] ^= c; c = t; }
-    }
-  }
-  if (rule == Z2D_FILL_EVEN_ODD) return p[0];
-  uint64_t a = 0;
-  for (int k = 0; k < 32; k++) a |= p[k];
-  return a;
-}
-
-Z2D_D uint64_t row_mask_any(const DevEdge* __restrict__ be, uint32_t n_be, int ys, int sx0, int ncols, uint32_t rule) {
-  if (n_be < 120) return row_mask<8>(be, n_be, ys, sx0, ncols, rule);
-  return row_mask_wide(be, n_be, ys, sx0, ncols, rule);
-}
-
-Z2D_D uint32_t nibble_popc(uint32_t x) {  // per-nibble popcount (values 0..4 in each 4-bit field)
-  x = x - ((x >> 1) & 0x55555555u);
-  return (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
-}
-
-__global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
-  __shared__ uint32_t tile_px[kRasterThreads / 32][8 * 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
-  if (gt >= A.n_tiles) return;
-  // tile -> surface, tx, ty
-  uint32_t si;
-  {
-    uint32_t lo = 0, hi = A.n_sfc;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (A.sfcs[mid].tile_base <= gt) lo = mid; else hi = mid;
-    }
-    si = lo;
-  }
-  const DevSurface S = A.sfcs[si];
-  const uint32_t lt = gt - S.tile_base;
-  const int ty = (int)(lt / (uint32_t)S.tiles_x), tx = (int)(lt % (uint32_t)S.tiles_x);
-  // ordered draw list of this tile-row
-  const uint32_t n_draws_s = S.draw_end - S.draw_begin;
-  const uint32_t chunks = (n_draws_s + kDrawChunk - 1) / kDrawChunk;
-  const uint32_t w0 = A.work_base[si] + (uint32_t)ty * chunks;
-  const uint32_t lb = A.list_off[w0], le = A.list_off[w0 + chunks];
-  if (lb == le) return;
-
-  uint32_t* px = tile_px[warp];
-  const int row = lane >> 1, half = lane & 1;
-  const int py = ty * kTile + row;
-  const int px0 = tx * kTile + half * 8;
-  bool loaded = false, dirty = false;
-  uint32_t n_cov = 0;
-  const size_t row_idx = (size_t)py * (size_t)S.w;
-
-  for (uint32_t base = lb; base < le; base += 32) {
-    uint2 it = make_uint2(0, 0);
-    bool hit = false;
-    if (base + lane < le) {
-      it = A.list_items[base + lane];
-      const int itx0 = (int)(it.y & 0xffffu), itx1 = (int)(it.y >> 16);
-      hit = tx >= itx0 && tx <= itx1;
-    }
-    uint32_t hits = __ballot_sync(0xffffffffu, hit);
-    while (hits) {
-      const int src_lane = __ffs(hits) - 1;
-      hits &= hits - 1;
-      const uint32_t di = __shfl_sync(0xffffffffu, it.x, src_lane);
-      const DevDraw& d = A.draws[di];
-
-      if (!loaded) {  // lazy tile load: 8 pixels per lane
-        for (int i = 0; i < 8; i++) {
-          const int x = px0 + i;
-          px[i * 32 + lane] = (x < S.w && py < S.h) ? load_raw(S.data, S.fmt, row_idx + (size_t)x) : 0u;
-        }
-        loaded = true;
-      }
-
-      // ---- coverage
-      const int aa = (int)d.aa;
-      const int Sc = (aa == Z2D_AA_NONE) ? 1 : 4;
-      uint32_t cov_e = 0, cov_o = 0;  // per-pixel coverage bytes: even pixels in cov_e, odd in cov_o
-      const bool in_rows = ty >= d.ey0 && ty <= d.ey1;
-      if (in_rows) {
-        const uint32_t bslot = d.band_base + (uint32_t)(ty - d.ey0);
-        const uint32_t eb = A.band_off[bslot], ee = A.band_off[bslot + 1];
-        const DevEdge* be = A.band_edges + eb;
-        const uint32_t nbe = ee - eb;
-        uint64_t m0 = 0, m1 = 0;
-        const int sx0 = tx * kTile * Sc;
-        if (Sc == 4) {
-          const int ys0 = ty * kTile * 4 + lane * 2;
-          m0 = row_mask_any(be, nbe, ys0, sx0, 64, d.rule);
-          m1 = row_mask_any(be, nbe, ys0 + 1, sx0, 64, d.rule);
-          // pixel row `row` needs sub-scanlines 4*row .. 4*row+3: this lane's two and its partner's two
-          const uint64_t q0 = __shfl_xor_sync(0xffffffffu, m0, 1), q1 = __shfl_xor_sync(0xffffffffu, m1, 1);
-          const int sh = half * 32;
-          const uint32_t a = nibble_popc((uint32_t)(m0 >> sh)), b = nibble_popc((uint32_t)(m1 >> sh));
-          const uint32_t c = nibble_popc((uint32_t)(q0 >> sh)), e2 = nibble_popc((uint32_t)(q1 >> sh));
-          cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
-          cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
-        } else {
-          m0 = row_mask_any(be, nbe, ty * kTile + row, sx0, 16, d.rule);
-          const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
-          for (int i = 0; i < 8; i += 2) {
-            cov_e |= ((bits >> i) & 1u) << (4 * i);        // byte i/2
-            cov_o |= ((bits >> (i + 1)) & 1u) << (4 * i);
-          }
-        }
-      }
-
-      // ---- composite the lane's 8 pixels
-      const bool pre = d.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
-      for (int i = 0; i < 8; i++) {
-        const int x = px0 + i;
-        if (x >= S.w || py >= S.h) continue;
-        uint32_t raw = px[i * 32 + lane];
-        if (pre) {  // multisample.zig:96-110
-          if (py < d.pre_y0 || (py > d.pre_y1 && py < d.pre_rows) || (py >= d.pre_y0 && py <= d.pre_y1 && x < d.pre_x)) raw = 0u;
-        }
-        if (x >= d.rx0 && x < d.rx1 && py >= d.ry0 && py < d.ry1) {
-          const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
-          n_cov += cov > 0;
-          raw = composite_cov(d, A.T, S.fmt, raw, cov, x, py);
-        }
-        px[i * 32 + lane] = raw;
-      }
-      dirty = true;
-    }
-  }
-  if (dirty) {
-    for (int i = 0; i < 8; i++) {
-      const int x = px0 + i;
-      if (x < S.w && py < S.h) store_raw(S.data, S.fmt, row_idx + (size_t)x, px[i * 32 + lane]);
-    }
-  }
-  if (A.counters) {
-    n_cov = __reduce_add_sync(0xffffffffu, n_cov);
-    if (lane == 0 && n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
-  }
-}
+}  // namespace z2d
+#include "raster.cuh"
+namespace z2d {
 
 // =====================================================================================
 // K5: surface-level compositor (SurfaceCompositor.run / StrideCompositor.run)
@@ -772,6 +512,107 @@ __global__ void __launch_bounds__(256) k_composite_v4(const __grid_constant__ Co
   }
 }
 
+// ---- fast path: ONE operator, no dst override, 32-bit destination, full contiguous rows,
+// source = single pixel or a same-width 32-bit surface.  The operator is a template constant
+// (the 28-way switch folds away), channel positions are uniform registers, u8->f32 decode is
+// a shared-memory table of the exact x/255.0f quotients, and each thread streams 2 x 128-bit
+// vectors per iteration.  HBM-bound: 8 B per pixel (read + write), +4 B with a surface source.
+struct Fmt32 {
+  int rs, gs, bs;
+  uint32_t has_a;
+};
+Z2D_D Fmt32 fmt32_of(uint32_t fmt) {
+  switch (fmt) {
+    case Z2D_FMT_ARGB: return {16, 8, 0, 1u};
+    case Z2D_FMT_XRGB: return {16, 8, 0, 0u};
+    case Z2D_FMT_RGB: return {0, 8, 16, 0u};
+    default: return {0, 8, 16, 1u};
+  }
+}
+Z2D_D RGBA16 unpack32(const Fmt32& f, uint32_t raw) {
+  return {(int)((raw >> f.rs) & 255u), (int)((raw >> f.gs) & 255u), (int)((raw >> f.bs) & 255u), f.has_a ? (int)(raw >> 24) : 255};
+}
+Z2D_D uint32_t pack32(const Fmt32& f, RGBA16 v) {
+  return (((uint32_t)v.r & 255u) << f.rs) | (((uint32_t)v.g & 255u) << f.gs) | (((uint32_t)v.b & 255u) << f.bs) |
+         (f.has_a ? (((uint32_t)v.a & 255u) << 24) : 0u);
+}
+
+template <int PREC, int OP, bool SURF>
+Z2D_D uint32_t fast_px(const Fmt32& fd, const Fmt32& fs, const float* __restrict__ lut, uint32_t raw, RGBA16 s_const, RGBAF sf_const,
+                       uint32_t sraw) {
+  RGBA16 d = unpack32(fd, raw);
+  if (PREC == Z2D_PRECISION_INTEGER) {
+    RGBA16 s = SURF ? unpack32(fs, sraw) : s_const;
+    return pack32(fd, int_op((uint32_t)OP, d, s));
+  }
+  RGBAF sf = sf_const;
+  if (SURF) {
+    RGBA16 s = unpack32(fs, sraw);
+    sf = {lut[s.r], lut[s.g], lut[s.b], lut[s.a]};
+  }
+  RGBAF df{lut[d.r], lut[d.g], lut[d.b], lut[d.a]};
+  return pack32(fd, encode_raw(float_op((uint32_t)OP, df, sf)));
+}
+
+template <int PREC, int OP, bool SURF>
+Z2D_D void fast_loop(const CompArgs& A, const float* __restrict__ lut) {
+  const Fmt32 fd = fmt32_of(A.fmt), fs = fmt32_of(A.ops[0].src.sfmt);
+  const RGBA16 sc = unpack_rgba(A.ops[0].src.px_rgba);
+  const RGBAF sfc{lut[sc.r], lut[sc.g], lut[sc.b], lut[sc.a]};
+  const size_t n4 = ((size_t)A.scan_w * (size_t)A.rows) >> 2;
+  uint4* __restrict__ dst = reinterpret_cast<uint4*>(A.data + ((size_t)A.dst_start_y * (size_t)A.w) * 4);
+  const uint4* __restrict__ src = SURF ? reinterpret_cast<const uint4*>(A.ops[0].src.sdata + ((size_t)A.src_start_y * (size_t)A.ops[0].src.sw) * 4) : nullptr;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {  // two independent 128-bit streams in flight per thread
+    uint4 a = dst[i], b = dst[i + stride];
+    uint4 sa = make_uint4(0, 0, 0, 0), sb = sa;
+    if (SURF) {
+      sa = __ldg(src + i);
+      sb = __ldg(src + i + stride);
+    }
+    a.x = fast_px<PREC, OP, SURF>(fd, fs, lut, a.x, sc, sfc, sa.x);
+    a.y = fast_px<PREC, OP, SURF>(fd, fs, lut, a.y, sc, sfc, sa.y);
+    a.z = fast_px<PREC, OP, SURF>(fd, fs, lut, a.z, sc, sfc, sa.z);
+    a.w = fast_px<PREC, OP, SURF>(fd, fs, lut, a.w, sc, sfc, sa.w);
+    b.x = fast_px<PREC, OP, SURF>(fd, fs, lut, b.x, sc, sfc, sb.x);
+    b.y = fast_px<PREC, OP, SURF>(fd, fs, lut, b.y, sc, sfc, sb.y);
+    b.z = fast_px<PREC, OP, SURF>(fd, fs, lut, b.z, sc, sfc, sb.z);
+    b.w = fast_px<PREC, OP, SURF>(fd, fs, lut, b.w, sc, sfc, sb.w);
+    dst[i] = a;
+    dst[i + stride] = b;
+  }
+  if (i < n4) {
+    uint4 a = dst[i];
+    uint4 sa = make_uint4(0, 0, 0, 0);
+    if (SURF) sa = __ldg(src + i);
+    a.x = fast_px<PREC, OP, SURF>(fd, fs, lut, a.x, sc, sfc, sa.x);
+    a.y = fast_px<PREC, OP, SURF>(fd, fs, lut, a.y, sc, sfc, sa.y);
+    a.z = fast_px<PREC, OP, SURF>(fd, fs, lut, a.z, sc, sfc, sa.z);
+    a.w = fast_px<PREC, OP, SURF>(fd, fs, lut, a.w, sc, sfc, sa.w);
+    dst[i] = a;
+  }
+}
+
+template <int PREC, bool SURF>
+__global__ void __launch_bounds__(256) k_composite_fast(const __grid_constant__ CompArgs A) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)threadIdx.x / 255.0f;  // color.zig:243-250 decodeRGBARaw, exact quotients
+  __syncthreads();
+  switch (A.ops[0].op) {
+#define Z2D_OPCASE(op) \
+  case op: fast_loop<PREC, op, SURF>(A, lut); break;
+    Z2D_OPCASE(Z2D_OP_CLEAR) Z2D_OPCASE(Z2D_OP_SRC) Z2D_OPCASE(Z2D_OP_DST) Z2D_OPCASE(Z2D_OP_SRC_OVER) Z2D_OPCASE(Z2D_OP_DST_OVER)
+    Z2D_OPCASE(Z2D_OP_SRC_IN) Z2D_OPCASE(Z2D_OP_DST_IN) Z2D_OPCASE(Z2D_OP_SRC_OUT) Z2D_OPCASE(Z2D_OP_DST_OUT) Z2D_OPCASE(Z2D_OP_SRC_ATOP)
+    Z2D_OPCASE(Z2D_OP_DST_ATOP) Z2D_OPCASE(Z2D_OP_XOR) Z2D_OPCASE(Z2D_OP_PLUS) Z2D_OPCASE(Z2D_OP_MULTIPLY) Z2D_OPCASE(Z2D_OP_SCREEN)
+    Z2D_OPCASE(Z2D_OP_OVERLAY) Z2D_OPCASE(Z2D_OP_DARKEN) Z2D_OPCASE(Z2D_OP_LIGHTEN) Z2D_OPCASE(Z2D_OP_COLOR_DODGE)
+    Z2D_OPCASE(Z2D_OP_COLOR_BURN) Z2D_OPCASE(Z2D_OP_HARD_LIGHT) Z2D_OPCASE(Z2D_OP_SOFT_LIGHT) Z2D_OPCASE(Z2D_OP_DIFFERENCE)
+    Z2D_OPCASE(Z2D_OP_EXCLUSION) Z2D_OPCASE(Z2D_OP_HUE) Z2D_OPCASE(Z2D_OP_SATURATION) Z2D_OPCASE(Z2D_OP_COLOR) Z2D_OPCASE(Z2D_OP_LUMINOSITY)
+#undef Z2D_OPCASE
+    default: break;
+  }
+}
+
 // whole-surface paint (Surface.paintPixel / initPixel) and single pixel put
 __global__ void k_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw) {
   if (fmt <= Z2D_FMT_RGBA) {
@@ -799,14 +640,14 @@ void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
                          DevEdge* edges, uint32_t* edge_draw, cudaStream_t st) {
   if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw);
 }
-void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, unsigned long long* counters, cudaStream_t st) {
-  if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, counters);
+void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {
+  if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, boxes, counters);
 }
 void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st) {
   if (n) k_reset_draws<<<blocks_for(n, 256), 256, 0, st>>>(draws, n);
 }
-void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, cudaStream_t st) {
-  if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off);
+void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st) {
+  if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off, hots);
 }
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st) {
   if (n) k_bin_count<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_count);
@@ -816,12 +657,12 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
   if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges);
 }
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
-                       const DevDraw* draws, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {
+                       const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {
   if (!n_work) return;
   if (write)
-    k_band_lists<true><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, draws, cnt, off, items);
+    k_band_lists<true><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, boxes, cnt, off, items);
   else
-    k_band_lists<false><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, draws, cnt, off, items);
+    k_band_lists<false><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, boxes, cnt, off, items);
 }
 void launch_raster(const RasterArgs& A, cudaStream_t st) {
   if (A.n_tiles) k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
@@ -834,6 +675,24 @@ void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   unsigned blocks = (unsigned)((items + 255) / 256);
   const unsigned cap = (unsigned)sm_count * 8u * 4u;  // grid-stride: a few waves of 8 resident CTAs per SM
   if (blocks > cap) blocks = cap;
+  const CompOp& o0 = A.ops[0];
+  const bool one = vec && A.n_ops == 1 && !o0.has_dst && o0.has_src;
+  const bool fast_px_src = one && o0.src.kind == Z2D_PARAM_PIXEL;
+  const bool fast_sfc_src = one && o0.src.kind == Z2D_PARAM_SURFACE && o0.src.sfmt <= Z2D_FMT_RGBA && o0.src.sw == A.w && A.src_start_x == 0;
+  if (fast_px_src || fast_sfc_src) {
+    unsigned fb = (unsigned)(((items + 1) / 2 + 255) / 256);  // two vectors per thread and iteration
+    const unsigned fcap = (unsigned)sm_count * 8u;             // persistent-style grid: 8 resident CTAs per SM
+    if (fb > fcap) fb = fcap;
+    if (fb == 0) fb = 1;
+    if (A.precision == Z2D_PRECISION_INTEGER) {
+      if (fast_px_src) k_composite_fast<Z2D_PRECISION_INTEGER, false><<<fb, 256, 0, st>>>(A);
+      else k_composite_fast<Z2D_PRECISION_INTEGER, true><<<fb, 256, 0, st>>>(A);
+    } else {
+      if (fast_px_src) k_composite_fast<Z2D_PRECISION_FLOAT, false><<<fb, 256, 0, st>>>(A);
+      else k_composite_fast<Z2D_PRECISION_FLOAT, true><<<fb, 256, 0, st>>>(A);
+    }
+    return;
+  }
   if (vec)
     k_composite_v4<<<blocks, 256, 0, st>>>(A);
   else

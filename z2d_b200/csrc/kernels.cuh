@@ -16,6 +16,7 @@ struct RasterArgs {
   const uint32_t* list_off;    // per work item (+1): offset into list_items
   const uint2* list_items;     // (draw index, tx0 | tx1 << 16), draw order within a tile-row
   const DevDraw* draws;
+  const DrawHot* hots;
   const uint32_t* band_off;    // per (draw, tile-row) slot (+1): offset into band_edges
   const DevEdge* band_edges;
   unsigned long long* counters;  // [0] covered pixels, [1] region pixels (may be null)
@@ -45,14 +46,14 @@ void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, cudaStream_t st);
-void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, unsigned long long* counters, cudaStream_t st);
+void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st);
 void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st);
-void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, cudaStream_t st);
+void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st);
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
                         uint32_t* band_cursor, DevEdge* band_edges, cudaStream_t st);
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
-                       const DevDraw* draws, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
+                       const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
 void launch_raster(const RasterArgs& A, cudaStream_t st);
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st);
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st);

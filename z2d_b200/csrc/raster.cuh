@@ -1,0 +1,371 @@
+// K4: fused coverage + compositing, one warp per 16x16-pixel tile (included by kernels.cu).
+//
+// For every draw that touches the tile, IN SUBMISSION ORDER:
+//   1. classify the draw's edges of this tile-row against the tile (warp-uniform):
+//      entirely right -> ignored; entirely left -> a per-sub-scanline scalar winding
+//      ("backdrop"); crossing -> evaluated exactly,
+//        x_i = round(x_start + x_inc * ((ys + 0.5) - top))          (Polygon.zig:302-307)
+//      and accumulated into bit-sliced winding counters (one 64-bit plane per bit, one bit
+//      per sample column), so that sample s is inside iff sum(dir | x_i <= s) != 0 / odd
+//      (Polygon.zig:326-353);
+//   2. popcount the 4x4 samples of each pixel -> coverage 0..16;
+//   3. composite the source into the tile (held in shared memory for the whole batch) with
+//      the draw's operator (shared.zig, multisample.zig:195-227, supersample.zig:159-184).
+// The tile is read from HBM once and written back once per batch.
+#pragma once
+
+namespace z2d {
+
+Z2D_D RGBA16 mask_mul16(RGBA16 s, int m) { return {iM(s.r, m), iM(s.g, m), iM(s.b, m), iM(s.a, m)}; }  // dst_in(dst:=s, src:=alpha8 m)
+
+// generic StrideCompositor batch: [dst_in(pattern, mask)]? ; op   (shared.zig:24-45, 78-102), any source / precision
+__device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables& T, uint32_t precision, uint32_t fmt, uint32_t raw,
+                                                   int mask8, bool use_mask, int x, int y) {
+  if (precision == Z2D_PRECISION_INTEGER) {
+    RGBA16 s = src_int(d.src, T, x, y, 0);
+    if (use_mask) s = mask_mul16(s, mask8);
+    return rgba16_to_raw(fmt, int_op_sw(d.op, raw_to_rgba16(fmt, raw), s));
+  }
+  RGBAF s = src_float(d.src, T, x, y, 0);
+  if (use_mask) {
+    const float ma = (float)mask8 / 255.0f;
+    s = {s.r * ma, s.g * ma, s.b * ma, ma * s.a};
+  }
+  RGBAF r = float_op(d.op, decode_raw(raw_to_rgba16(fmt, raw)), s);
+  return rgba16_to_raw(fmt, encode_raw(r));
+}
+
+// cov: number of covered samples (MSAA/SSAA: 0..16, none: 0..1).  Returns the new raw pixel.
+Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTables& T, uint32_t fmt, uint32_t raw, int cov, int x, int y) {
+  int mask;
+  bool use_mask;
+  if (h.aa == Z2D_AA_SUPERSAMPLE_4X) {
+    // mask = box average of 16 samples in the mask surface's own format (supersample.zig:82-91, pixel.zig:435-464,633-646)
+    if (fmt == Z2D_FMT_ALPHA4 || fmt == Z2D_FMT_ALPHA2 || fmt == Z2D_FMT_ALPHA1) {
+      const int bits = fmt_bits(fmt);
+      mask = scale_alpha((((1 << bits) - 1) * cov) / 16, bits, 8);
+    } else {
+      mask = (255 * cov) / 16;
+    }
+    use_mask = true;
+    if (h.src_kind == Z2D_PARAM_PIXEL && h.precision == Z2D_PRECISION_INTEGER)
+      return rgba16_to_raw(fmt, int_op_sw(h.op, raw_to_rgba16(fmt, raw), mask_mul16(unpack_rgba(h.px_rgba), mask)));
+    return composite_generic(d, T, h.precision, fmt, raw, mask, true, x, y);
+  }
+  if (cov == 0) return raw;
+  if (h.op == Z2D_OP_CLEAR) return 0u;  // shared.zig:18,60 (also at partial coverage)
+  if (h.aa == Z2D_AA_NONE || cov == 16) {
+    if (h.reduces) return h.paint_raw;  // Surface.paintStride
+    mask = 255;
+    use_mask = false;
+  } else {
+    mask = 16 * cov - 1;  // multisample.zig:223
+    use_mask = true;
+  }
+  // opaque-pixel fast path of the reference is integer-only (surface.zig:557-581)
+  const uint32_t prec = h.reduces ? (uint32_t)Z2D_PRECISION_INTEGER : h.precision;
+  if (h.src_kind == Z2D_PARAM_PIXEL && prec == Z2D_PRECISION_INTEGER) {
+    RGBA16 s = unpack_rgba(h.px_rgba);
+    if (use_mask) s = mask_mul16(s, mask);
+    return rgba16_to_raw(fmt, int_op_sw(h.op, raw_to_rgba16(fmt, raw), s));
+  }
+  return composite_generic(d, T, prec, fmt, raw, mask, use_mask, x, y);
+}
+
+// ------------------------------------------------------------------------- coverage
+template <int W>
+Z2D_D void wind_add(uint64_t (&p)[W], uint64_t mask, bool up) {
+  uint64_t c = mask;
+  if (up) {  // +1 on every column >= col
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      const uint64_t t = p[k] & c;
+      p[k] ^= c;
+      c = t;
+    }
+  } else {  // -1
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      const uint64_t t = ~p[k] & c;
+      p[k] ^= c;
+      c = t;
+    }
+  }
+}
+
+Z2D_D double4 ld_edge(const DevEdge* e) {  // 2 x 128-bit read-only loads (warp-uniform address)
+  const double2* q = reinterpret_cast<const double2*>(e);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// Column (relative to the tile's first sample) at which the edge crosses the sub-scanline
+// centre ym, or -1 when the edge is inactive there / crosses right of the tile.
+Z2D_D int edge_col(const double4& ev, double top, double bottom, double ym, int sx0, int ncols) {
+  if (!(top < ym && ym <= bottom)) return -1;                     // Polygon.zig:284-285
+  const double xf = round_half_away(ev.z + (ev.w * (ym - top)));  // Polygon.zig:305
+  const double cf = xf - (double)sx0;
+  if (!(cf < (double)ncols)) return -1;
+  return cf < 0.0 ? 0 : (int)cf;
+}
+
+struct EdgeClass {
+  double top, bottom;
+  bool down;
+  int side;  // -1 entirely left of the tile, +1 entirely right, 0 crossing
+};
+Z2D_D EdgeClass classify(const double4& ev, double xl, double xr) {
+  EdgeClass c;
+  c.down = ev.x < ev.y;
+  c.top = c.down ? ev.x : ev.y;
+  c.bottom = c.down ? ev.y : ev.x;
+  // x along the edge is monotone between x_start and its value at the bottom; rounding moves it by <= 0.5
+  const double xe = ev.z + ev.w * (c.bottom - c.top);
+  const double xmin = ev.z < xe ? ev.z : xe, xmax = ev.z < xe ? xe : ev.z;
+  c.side = (xmin > xr) ? 1 : ((xmax < xl) ? -1 : 0);
+  return c;
+}
+
+template <int W>
+Z2D_D void cross_pass(const DevEdge* __restrict__ be, uint32_t n_be, double ym0, double ym1, bool two, double xl, double xr, int sx0,
+                      int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1) {
+  uint64_t p0[W], p1[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) {  // start from the backdrop winding (two's complement, bit-sliced)
+    p0[k] = ((wl0 >> k) & 1) ? ~0ull : 0ull;
+    p1[k] = ((wl1 >> k) & 1) ? ~0ull : 0ull;
+  }
+  for (uint32_t i = 0; i < n_be; i++) {
+    const double4 ev = ld_edge(be + i);
+    const EdgeClass c = classify(ev, xl, xr);
+    if (c.side != 0) continue;
+    const int c0 = edge_col(ev, c.top, c.bottom, ym0, sx0, ncols);
+    if (c0 >= 0) {
+      const uint64_t mask = ~0ull << c0;
+      if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, !c.down);
+    }
+    if (two) {
+      const int c1 = edge_col(ev, c.top, c.bottom, ym1, sx0, ncols);
+      if (c1 >= 0) {
+        const uint64_t mask = ~0ull << c1;
+        if (even_odd) p1[0] ^= mask; else wind_add<W>(p1, mask, !c.down);
+      }
+    }
+  }
+  if (even_odd) {
+    m0 = p0[0];
+    m1 = p1[0];
+  } else {
+    uint64_t a = 0, b = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      a |= p0[k];
+      b |= p1[k];
+    }
+    m0 = a;
+    m1 = b;
+  }
+}
+
+// rare: more than 60 edges of one draw cross one tile; 32 planes in local memory, one row at a time
+__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, uint32_t n_be, double ym, double xl, double xr, int sx0,
+                                                int ncols, bool even_odd, int wl) {
+  uint64_t p[32];
+  for (int k = 0; k < 32; k++) p[k] = ((wl >> k) & 1) ? ~0ull : 0ull;
+  for (uint32_t i = 0; i < n_be; i++) {
+    const double4 ev = ld_edge(be + i);
+    const EdgeClass c = classify(ev, xl, xr);
+    if (c.side != 0) continue;
+    const int col = edge_col(ev, c.top, c.bottom, ym, sx0, ncols);
+    if (col < 0) continue;
+    uint64_t cy = ~0ull << col;
+    if (even_odd) {
+      p[0] ^= cy;
+    } else if (!c.down) {
+      for (int k = 0; k < 32 && cy; k++) { const uint64_t t = p[k] & cy; p[k] ^= cy; cy = t; }
+    } else {
+      for (int k = 0; k < 32 && cy; k++) { const uint64_t t = ~p[k] & cy; p[k] ^= cy; cy = t; }
+    }
+  }
+  if (even_odd) return p[0];
+  uint64_t a = 0;
+  for (int k = 0; k < 32; k++) a |= p[k];
+  return a;
+}
+
+// Inside-masks of this lane's sub-scanlines ys0 (and ys0+1 when `two`) for one draw in one tile.
+Z2D_D void tile_cover(const DevEdge* __restrict__ be, uint32_t n_be, int ys0, bool two, int sx0, int ncols, uint32_t rule, uint64_t& m0,
+                      uint64_t& m1) {
+  const double ym0 = (double)ys0 + 0.5, ym1 = (double)ys0 + 1.5;
+  const double xl = (double)sx0 - 1.0, xr = (double)(sx0 + ncols) + 1.0;
+  const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
+  int wl0 = 0, wl1 = 0;
+  uint32_t ncross = 0;
+  for (uint32_t i = 0; i < n_be; i++) {  // pass 1: backdrop from the edges left of the tile, count the crossing ones
+    const double4 ev = ld_edge(be + i);
+    const EdgeClass c = classify(ev, xl, xr);
+    if (c.side > 0) continue;
+    if (c.side < 0) {
+      const int dir = c.down ? -1 : 1;
+      if (c.top < ym0 && ym0 <= c.bottom) wl0 += dir;
+      if (two && c.top < ym1 && ym1 <= c.bottom) wl1 += dir;
+    } else {
+      ncross++;  // warp-uniform
+    }
+  }
+  if (ncross == 0) {
+    m0 = (even_odd ? (wl0 & 1) : (wl0 != 0)) ? ~0ull : 0ull;
+    m1 = (even_odd ? (wl1 & 1) : (wl1 != 0)) ? ~0ull : 0ull;
+    return;
+  }
+  // |sum over crossing edges| <= ncross: a backdrop beyond that keeps the whole row inside (non-zero rule)
+  const bool full0 = !even_odd && (wl0 > (int)ncross || -wl0 > (int)ncross);
+  const bool full1 = !even_odd && (wl1 > (int)ncross || -wl1 > (int)ncross);
+  const int b0 = full0 ? 0 : wl0, b1 = full1 ? 0 : wl1;
+  if (ncross <= 7) {
+    cross_pass<5>(be, n_be, ym0, ym1, two, xl, xr, sx0, ncols, even_odd, b0, b1, m0, m1);
+  } else if (ncross <= 60) {
+    cross_pass<8>(be, n_be, ym0, ym1, two, xl, xr, sx0, ncols, even_odd, b0, b1, m0, m1);
+  } else {
+    m0 = cross_row_wide(be, n_be, ym0, xl, xr, sx0, ncols, even_odd, b0);
+    m1 = two ? cross_row_wide(be, n_be, ym1, xl, xr, sx0, ncols, even_odd, b1) : 0ull;
+  }
+  if (full0) m0 = ~0ull;
+  if (full1) m1 = ~0ull;
+}
+
+Z2D_D uint32_t nibble_popc(uint32_t x) {  // per-nibble popcount (values 0..4 in each 4-bit field)
+  x = x - ((x >> 1) & 0x55555555u);
+  return (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+}
+
+__global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
+  __shared__ uint32_t tile_px[kRasterThreads / 32][8 * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
+  if (gt >= A.n_tiles) return;
+  // tile -> surface, tx, ty
+  uint32_t si;
+  {
+    uint32_t lo = 0, hi = A.n_sfc;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (A.sfcs[mid].tile_base <= gt) lo = mid; else hi = mid;
+    }
+    si = lo;
+  }
+  const DevSurface S = A.sfcs[si];
+  const uint32_t lt = gt - S.tile_base;
+  const int ty = (int)(lt / (uint32_t)S.tiles_x), tx = (int)(lt % (uint32_t)S.tiles_x);
+  // ordered draw list of this tile-row
+  const uint32_t n_draws_s = S.draw_end - S.draw_begin;
+  const uint32_t chunks = (n_draws_s + kDrawChunk - 1) / kDrawChunk;
+  const uint32_t w0 = A.work_base[si] + (uint32_t)ty * chunks;
+  const uint32_t lb = A.list_off[w0], le = A.list_off[w0 + chunks];
+  if (lb == le) return;
+
+  uint32_t* px = tile_px[warp];
+  const int row = lane >> 1, half = lane & 1;
+  const int py = ty * kTile + row;
+  const int px0 = tx * kTile + half * 8;
+  bool loaded = false, dirty = false;
+  uint32_t n_cov = 0;
+  const size_t row_idx = (size_t)py * (size_t)S.w;
+  const bool row_ok = py < S.h;
+
+  for (uint32_t base = lb; base < le; base += 32) {
+    uint2 it = make_uint2(0, 0);
+    bool hit = false;
+    if (base + lane < le) {
+      it = A.list_items[base + lane];
+      const int itx0 = (int)(it.y & 0xffffu), itx1 = (int)(it.y >> 16);
+      hit = tx >= itx0 && tx <= itx1;
+    }
+    uint32_t hits = __ballot_sync(0xffffffffu, hit);
+    while (hits) {
+      const int src_lane = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const uint32_t di = __shfl_sync(0xffffffffu, it.x, src_lane);
+      const DrawHot h = A.hots[di];
+
+      // ---- coverage
+      const int aa = (int)h.aa;
+      const int Sc = (aa == Z2D_AA_NONE) ? 1 : 4;
+      uint32_t cov_e = 0, cov_o = 0;  // per-pixel coverage bytes: even pixels in cov_e, odd in cov_o
+      const bool in_rows = ty >= h.ey0 && ty <= h.ey1;
+      const bool pre = h.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
+      const bool all_px = aa == Z2D_AA_SUPERSAMPLE_4X;  // every pixel of the region is composited, even at coverage 0
+      if (!in_rows && !pre) continue;
+      if (in_rows) {
+        const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
+        const uint32_t eb = A.band_off[bslot], ee = A.band_off[bslot + 1];
+        const DevEdge* be = A.band_edges + eb;
+        const uint32_t nbe = ee - eb;
+        uint64_t m0 = 0, m1 = 0;
+        const int sx0 = tx * kTile * Sc;
+        if (Sc == 4) {
+          tile_cover(be, nbe, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, m0, m1);
+          // pixel row `row` needs sub-scanlines 4*row .. 4*row+3: this lane's two and its partner's two
+          const uint64_t q0 = __shfl_xor_sync(0xffffffffu, m0, 1), q1 = __shfl_xor_sync(0xffffffffu, m1, 1);
+          const int sh = half * 32;
+          const uint32_t a = nibble_popc((uint32_t)(m0 >> sh)), b = nibble_popc((uint32_t)(m1 >> sh));
+          const uint32_t c = nibble_popc((uint32_t)(q0 >> sh)), e2 = nibble_popc((uint32_t)(q1 >> sh));
+          cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
+          cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
+        } else {
+          tile_cover(be, nbe, ty * kTile + row, false, sx0, 16, h.rule, m0, m1);
+          const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
+          for (int i = 0; i < 8; i += 2) {
+            cov_e |= ((bits >> i) & 1u) << (4 * i);  // byte i/2
+            cov_o |= ((bits >> (i + 1)) & 1u) << (4 * i);
+          }
+        }
+      }
+      // nothing of this draw lands in the tile?
+      const bool lane_work = row_ok && (pre || (py >= h.ry0 && py < h.ry1 && (all_px || (cov_e | cov_o) != 0u)));
+      if (!__any_sync(0xffffffffu, lane_work)) continue;
+
+      if (!loaded) {  // lazy tile load: 8 pixels per lane
+        for (int i = 0; i < 8; i++) {
+          const int x = px0 + i;
+          px[i * 32 + lane] = (x < S.w && row_ok) ? load_raw(S.data, S.fmt, row_idx + (size_t)x) : 0u;
+        }
+        loaded = true;
+      }
+
+      // ---- composite the lane's 8 pixels
+      const DevDraw& d = A.draws[di];
+      for (int i = 0; i < 8; i++) {
+        const int x = px0 + i;
+        const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
+        const bool in_sfc = x < S.w && row_ok;
+        const bool in_reg = in_sfc && x >= h.rx0 && x < h.rx1 && py >= h.ry0 && py < h.ry1;
+        const bool work = in_sfc && (pre || (in_reg && (all_px || cov != 0)));
+        if (!__any_sync(0xffffffffu, work)) continue;
+        if (!work) continue;
+        uint32_t raw = px[i * 32 + lane];
+        if (pre) {  // multisample.zig:96-110
+          if (py < h.pre_y0 || (py > h.pre_y1 && py < h.pre_rows) || (py >= h.pre_y0 && py <= h.pre_y1 && x < h.pre_x)) raw = 0u;
+        }
+        if (in_reg) {
+          n_cov += cov > 0;
+          raw = composite_cov(h, d, A.T, S.fmt, raw, cov, x, py);
+        }
+        px[i * 32 + lane] = raw;
+      }
+      dirty = true;
+    }
+  }
+  if (dirty) {
+    for (int i = 0; i < 8; i++) {
+      const int x = px0 + i;
+      if (x < S.w && row_ok) store_raw(S.data, S.fmt, row_idx + (size_t)x, px[i * 32 + lane]);
+    }
+  }
+  if (A.counters) {
+    n_cov = __reduce_add_sync(0xffffffffu, n_cov);
+    if (lane == 0 && n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
+  }
+}
+
+}  // namespace z2d

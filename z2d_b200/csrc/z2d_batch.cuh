@@ -69,6 +69,21 @@ struct DevEdge {
   double y0, y1, x_start, x_inc;
 };
 
+// Compact per-draw records written by k_setup_draws: the tile-row lists only need the
+// tile box, the raster kernel only the fields below (the 300-byte DevDraw is touched
+// again only for gradient / dither sources).
+struct DrawBox {  // tx0 < 0 => draw not valid
+  int32_t tx0, tx1, ty0, ty1;
+};
+struct DrawHot {
+  uint32_t aa, rule, op, precision;
+  uint32_t reduces, paint_raw, px_rgba, src_kind;
+  int32_t rx0, rx1, ry0, ry1;
+  int32_t ey0, ey1;
+  uint32_t band_base, unbounded;
+  int32_t pre_y0, pre_y1, pre_x, pre_rows;
+};
+
 // order-preserving f64 <-> i64 (for atomicMin / atomicMax on extents)
 Z2D_HD long long f64_order(double v) {
   long long b;

@@ -227,6 +227,42 @@ Z2D_HD RGBA16 int_op(uint32_t op, RGBA16 d, RGBA16 s) {
           int_op_alpha(op, s.a, d.a)};
 }
 
+// Same operator table with ONE dispatch per pixel instead of one per channel (for call sites
+// where `op` is a run-time, warp-uniform value).
+#define Z2D_CH3(EXPR, AEXPR)                                                       \
+  {                                                                                \
+    auto f = [&](int sc, int dc) -> int { return EXPR; };                          \
+    return RGBA16{f(s.r, d.r), f(s.g, d.g), f(s.b, d.b), AEXPR};                   \
+  }
+Z2D_HD RGBA16 int_op_sw(uint32_t op, RGBA16 d, RGBA16 s) {
+  const int sa = s.a, da = d.a;
+  const int so = sa + da - iM(sa, da);
+  switch (op) {
+    case Z2D_OP_SRC: return s;
+    case Z2D_OP_DST: return d;
+    case Z2D_OP_SRC_OVER: Z2D_CH3(sc + iIM(dc, sa), so)
+    case Z2D_OP_DST_OVER: Z2D_CH3(dc + iIM(sc, da), so)
+    case Z2D_OP_SRC_IN: Z2D_CH3(iM(sc, da), iM(sa, da))
+    case Z2D_OP_DST_IN: Z2D_CH3(iM(dc, sa), iM(sa, da))
+    case Z2D_OP_SRC_OUT: Z2D_CH3(iIM(sc, da), iIM(sa, da))
+    case Z2D_OP_DST_OUT: Z2D_CH3(iIM(dc, sa), iIM(da, sa))
+    case Z2D_OP_SRC_ATOP: Z2D_CH3(iM(sc, da) + iIM(dc, sa), da)
+    case Z2D_OP_DST_ATOP: Z2D_CH3(iM(dc, sa) + iIM(sc, da), sa)
+    case Z2D_OP_XOR: Z2D_CH3(iIM(sc, da) + iIM(dc, sa), iIM(sa, da) + iIM(da, sa))
+    case Z2D_OP_PLUS: Z2D_CH3(imin(255, sc + dc), imin(255, sa + da))
+    case Z2D_OP_MULTIPLY: Z2D_CH3(iM(sc, dc) + iIM(sc, da) + iIM(dc, sa), so)
+    case Z2D_OP_SCREEN: Z2D_CH3(sc + dc - iM(sc, dc), so)
+    case Z2D_OP_OVERLAY: Z2D_CH3((2 * dc <= da) ? iM(2 * sc, dc) + iIM(sc, da) + iIM(dc, sa) : iRM(sc, da) + iRM(dc, sa) - iM(2 * dc, sc) - iM(da, sa), so)
+    case Z2D_OP_DARKEN: Z2D_CH3(imin(iM(sc, da), iM(dc, sa)) + iIM(sc, da) + iIM(dc, sa), so)
+    case Z2D_OP_LIGHTEN: Z2D_CH3(imax(iM(sc, da), iM(dc, sa)) + iIM(sc, da) + iIM(dc, sa), so)
+    case Z2D_OP_HARD_LIGHT: Z2D_CH3((2 * sc <= sa) ? iM(2 * sc, dc) + iIM(sc, da) + iIM(dc, sa) : iRM(sc, da) + iRM(dc, sa) - iM(sa, da) - iM(2 * sc, dc), so)
+    case Z2D_OP_DIFFERENCE: Z2D_CH3(sc + dc - 2 * imin(iM(sc, da), iM(dc, sa)), so)
+    case Z2D_OP_EXCLUSION: Z2D_CH3((iM(sc, da) + iM(dc, sa) - 2 * iM(sc, dc)) + iIM(sc, da) + iIM(dc, sa), so)
+    default: return RGBA16{0, 0, 0, 0};
+  }
+}
+#undef Z2D_CH3
+
 // ------------------------------------------------------------ float operators
 Z2D_HD float fminz(float a, float b) { return b < a ? b : a; }  // std::min / Zig @min on non-NaN; NaN in b -> a
 Z2D_HD float fmaxz(float a, float b) { return a < b ? b : a; }

@@ -113,7 +113,7 @@ struct z2d_ctx {
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
   DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
   uint32_t* h_total = nullptr;  // pinned readback slot
-  DevBuf d_counters;
+  DevBuf d_counters, d_boxes, d_hots;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   BatchMeta last;
   bool stats_pending = false;
@@ -363,7 +363,9 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
   // K2: per-draw regions; (draw, tile-row) slots
   CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
-  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(),
+  CK(c, c->d_boxes.ensure((size_t)n_draws * sizeof(DrawBox) + 16));
+  CK(c, c->d_hots.ensure((size_t)n_draws * sizeof(DrawHot) + 16));
+  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(), c->d_boxes.as<DrawBox>(),
                      c->d_counters.as<unsigned long long>(), st);
   CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
   uint32_t n_slots = 0;
@@ -371,7 +373,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     int rc = read_total(c, c->d_draw_band_off.as<uint32_t>() + n_draws, n_slots);
     if (rc) return rc;
   }
-  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), st);
+  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), st);
 
   // K3a: edges -> (draw, tile-row) lists
   CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
@@ -392,7 +394,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
   // K3b: ordered draw list per surface tile-row
   CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
-  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(),
+  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_boxes.as<DrawBox>(),
                     c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
   uint32_t n_items = 0;
@@ -401,7 +403,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     if (rc) return rc;
   }
   CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
-  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_draws.as<DevDraw>(), nullptr,
+  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_boxes.as<DrawBox>(), nullptr,
                     c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
@@ -414,6 +416,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.list_off = c->d_list_off.as<uint32_t>();
   A.list_items = c->d_list_items.as<uint2>();
   A.draws = c->d_draws.as<DevDraw>();
+  A.hots = c->d_hots.as<DrawHot>();
   A.band_off = c->d_band_off.as<uint32_t>();
   A.band_edges = c->d_band_edges.as<DevEdge>();
   A.counters = c->d_counters.as<unsigned long long>();
@@ -625,6 +628,8 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   c->draws.release();
   if (c->h_total) cudaFreeHost(c->h_total);
   c->d_counters.release();
+  c->d_boxes.release();
+  c->d_hots.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
