@@ -393,7 +393,7 @@ __global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* _
 
 __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
                               const DevDraw* __restrict__ draws, const uint32_t* __restrict__ band_off,
-                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges) {
+                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges, int4* __restrict__ band_hdr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
   const DevDraw& d = draws[edge_draw[i]];
@@ -401,10 +401,25 @@ __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t*
   const DevEdge e = edges[i];
   int t0, t1;
   if (!edge_band_range(e, d, t0, t1)) return;
+  // integer header for the raster kernel's classification pass:
+  //   x = conservative sample-column range [xlo, xhi] of every rounded crossing of this edge,
+  //   z = first active sub-scanline (bit 31 set for an up edge, dir = +1), w = last active sub-scanline
+  const bool down = e.y0 < e.y1;
+  const double top = down ? e.y0 : e.y1, bottom = down ? e.y1 : e.y0;
+  const double xe = e.x_start + e.x_inc * (bottom - top);
+  const double xmin = e.x_start < xe ? e.x_start : xe, xmax = e.x_start < xe ? xe : e.x_start;
+  const double big = 1.0e9;
+  const double ya = fmax(floor(top - 0.5) + 1.0, 0.0), yb = fmin(floor(bottom - 0.5), big);
+  int4 h;
+  h.x = (int)fmax(fmin(floor(xmin) - 1.0, big), -big);
+  h.y = (int)fmax(fmin(ceil(xmax) + 1.0, big), -big);
+  h.z = (int)fmin(ya, big) | (down ? 0 : (int)0x80000000);
+  h.w = (int)fmax(yb, -1.0);
   for (int t = t0; t <= t1; t++) {
     const uint32_t b = d.band_base + (uint32_t)(t - d.ey0);
     const uint32_t slot = band_off[b] + atomicAdd(&band_cursor[b], 1u);
     band_edges[slot] = e;
+    band_hdr[slot] = h;
   }
 }
 
@@ -517,26 +532,6 @@ __global__ void __launch_bounds__(256) k_composite_v4(const __grid_constant__ Co
 // (the 28-way switch folds away), channel positions are uniform registers, u8->f32 decode is
 // a shared-memory table of the exact x/255.0f quotients, and each thread streams 2 x 128-bit
 // vectors per iteration.  HBM-bound: 8 B per pixel (read + write), +4 B with a surface source.
-struct Fmt32 {
-  int rs, gs, bs;
-  uint32_t has_a;
-};
-Z2D_D Fmt32 fmt32_of(uint32_t fmt) {
-  switch (fmt) {
-    case Z2D_FMT_ARGB: return {16, 8, 0, 1u};
-    case Z2D_FMT_XRGB: return {16, 8, 0, 0u};
-    case Z2D_FMT_RGB: return {0, 8, 16, 0u};
-    default: return {0, 8, 16, 1u};
-  }
-}
-Z2D_D RGBA16 unpack32(const Fmt32& f, uint32_t raw) {
-  return {(int)((raw >> f.rs) & 255u), (int)((raw >> f.gs) & 255u), (int)((raw >> f.bs) & 255u), f.has_a ? (int)(raw >> 24) : 255};
-}
-Z2D_D uint32_t pack32(const Fmt32& f, RGBA16 v) {
-  return (((uint32_t)v.r & 255u) << f.rs) | (((uint32_t)v.g & 255u) << f.gs) | (((uint32_t)v.b & 255u) << f.bs) |
-         (f.has_a ? (((uint32_t)v.a & 255u) << 24) : 0u);
-}
-
 template <int PREC, int OP, bool SURF>
 Z2D_D uint32_t fast_px(const Fmt32& fd, const Fmt32& fs, const float* __restrict__ lut, uint32_t raw, RGBA16 s_const, RGBAF sf_const,
                        uint32_t sraw) {
@@ -653,8 +648,8 @@ void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t 
   if (n) k_bin_count<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_count);
 }
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
-                        uint32_t* band_cursor, DevEdge* band_edges, cudaStream_t st) {
-  if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges);
+                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st) {
+  if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges, band_hdr);
 }
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
                        const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {

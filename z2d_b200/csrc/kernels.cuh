@@ -19,6 +19,7 @@ struct RasterArgs {
   const DrawHot* hots;
   const uint32_t* band_off;    // per (draw, tile-row) slot (+1): offset into band_edges
   const DevEdge* band_edges;
+  const int4* band_hdr;        // per binned edge: {xlo, xhi, first row | dir<<31, last row}
   unsigned long long* counters;  // [0] covered pixels, [1] region pixels (may be null)
   GradTables T;
 };
@@ -51,7 +52,7 @@ void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st);
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st);
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
-                        uint32_t* band_cursor, DevEdge* band_edges, cudaStream_t st);
+                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st);
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
                        const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
 void launch_raster(const RasterArgs& A, cudaStream_t st);

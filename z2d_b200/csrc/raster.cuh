@@ -1,9 +1,9 @@
 // K4: fused coverage + compositing, one warp per 16x16-pixel tile (included by kernels.cu).
 //
 // For every draw that touches the tile, IN SUBMISSION ORDER:
-//   1. classify the draw's edges of this tile-row against the tile (warp-uniform):
-//      entirely right -> ignored; entirely left -> a per-sub-scanline scalar winding
-//      ("backdrop"); crossing -> evaluated exactly,
+//   1. classify the draw's edges of this tile-row against the tile from their integer
+//      headers (warp-uniform): entirely right -> ignored; entirely left -> a per-sub-scanline
+//      scalar winding ("backdrop"); crossing -> evaluated exactly,
 //        x_i = round(x_start + x_inc * ((ys + 0.5) - top))          (Polygon.zig:302-307)
 //      and accumulated into bit-sliced winding counters (one 64-bit plane per bit, one bit
 //      per sample column), so that sample s is inside iff sum(dir | x_i <= s) != 0 / odd
@@ -35,8 +35,39 @@ __device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradT
   return rgba16_to_raw(fmt, encode_raw(r));
 }
 
+// 32-bit formats: channel positions as uniform registers (no per-pixel format switch)
+struct Fmt32 {
+  int rs, gs, bs;
+  uint32_t has_a;
+};
+Z2D_D Fmt32 fmt32_of(uint32_t fmt) {
+  switch (fmt) {
+    case Z2D_FMT_ARGB: return {16, 8, 0, 1u};
+    case Z2D_FMT_XRGB: return {16, 8, 0, 0u};
+    case Z2D_FMT_RGB: return {0, 8, 16, 0u};
+    default: return {0, 8, 16, 1u};
+  }
+}
+Z2D_D RGBA16 unpack32(const Fmt32& f, uint32_t raw) {
+  return {(int)((raw >> f.rs) & 255u), (int)((raw >> f.gs) & 255u), (int)((raw >> f.bs) & 255u), f.has_a ? (int)(raw >> 24) : 255};
+}
+Z2D_D uint32_t pack32(const Fmt32& f, RGBA16 v) {
+  return (((uint32_t)v.r & 255u) << f.rs) | (((uint32_t)v.g & 255u) << f.gs) | (((uint32_t)v.b & 255u) << f.bs) |
+         (f.has_a ? (((uint32_t)v.a & 255u) << 24) : 0u);
+}
+
+struct TileFmt {
+  uint32_t fmt;
+  bool is32;
+  Fmt32 f;
+};
+Z2D_D RGBA16 tf_unpack(const TileFmt& t, uint32_t raw) { return t.is32 ? unpack32(t.f, raw) : raw_to_rgba16(t.fmt, raw); }
+Z2D_D uint32_t tf_pack(const TileFmt& t, RGBA16 v) { return t.is32 ? pack32(t.f, v) : rgba16_to_raw(t.fmt, v); }
+
 // cov: number of covered samples (MSAA/SSAA: 0..16, none: 0..1).  Returns the new raw pixel.
-Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTables& T, uint32_t fmt, uint32_t raw, int cov, int x, int y) {
+Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTables& T, const TileFmt& tf, RGBA16 spx, uint32_t raw, int cov,
+                             int x, int y) {
+  const uint32_t fmt = tf.fmt;
   int mask;
   bool use_mask;
   if (h.aa == Z2D_AA_SUPERSAMPLE_4X) {
@@ -47,9 +78,8 @@ Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTable
     } else {
       mask = (255 * cov) / 16;
     }
-    use_mask = true;
     if (h.src_kind == Z2D_PARAM_PIXEL && h.precision == Z2D_PRECISION_INTEGER)
-      return rgba16_to_raw(fmt, int_op_sw(h.op, raw_to_rgba16(fmt, raw), mask_mul16(unpack_rgba(h.px_rgba), mask)));
+      return tf_pack(tf, int_op_sw(h.op, tf_unpack(tf, raw), mask_mul16(spx, mask)));
     return composite_generic(d, T, h.precision, fmt, raw, mask, true, x, y);
   }
   if (cov == 0) return raw;
@@ -62,12 +92,12 @@ Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTable
     mask = 16 * cov - 1;  // multisample.zig:223
     use_mask = true;
   }
-  // opaque-pixel fast path of the reference is integer-only (surface.zig:557-581)
+  // the opaque-pixel fast path of the reference is integer-only (surface.zig:557-581)
   const uint32_t prec = h.reduces ? (uint32_t)Z2D_PRECISION_INTEGER : h.precision;
   if (h.src_kind == Z2D_PARAM_PIXEL && prec == Z2D_PRECISION_INTEGER) {
-    RGBA16 s = unpack_rgba(h.px_rgba);
+    RGBA16 s = spx;
     if (use_mask) s = mask_mul16(s, mask);
-    return rgba16_to_raw(fmt, int_op_sw(h.op, raw_to_rgba16(fmt, raw), s));
+    return tf_pack(tf, int_op_sw(h.op, tf_unpack(tf, raw), s));
   }
   return composite_generic(d, T, prec, fmt, raw, mask, use_mask, x, y);
 }
@@ -99,89 +129,92 @@ Z2D_D double4 ld_edge(const DevEdge* e) {  // 2 x 128-bit read-only loads (warp-
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// Column (relative to the tile's first sample) at which the edge crosses the sub-scanline
-// centre ym, or -1 when the edge is inactive there / crosses right of the tile.
-Z2D_D int edge_col(const double4& ev, double top, double bottom, double ym, int sx0, int ncols) {
-  if (!(top < ym && ym <= bottom)) return -1;                     // Polygon.zig:284-285
-  const double xf = round_half_away(ev.z + (ev.w * (ym - top)));  // Polygon.zig:305
+// Column (relative to the tile's first sample) at which an ACTIVE edge crosses the sub-scanline
+// centre ys + 0.5, or -1 when that is right of the tile.
+Z2D_D int edge_col(const double4& ev, double top, int ys, int sx0, int ncols) {
+  const double xf = round_half_away(ev.z + (ev.w * (((double)ys + 0.5) - top)));  // Polygon.zig:305
   const double cf = xf - (double)sx0;
   if (!(cf < (double)ncols)) return -1;
   return cf < 0.0 ? 0 : (int)cf;
 }
 
-struct EdgeClass {
-  double top, bottom;
-  bool down;
-  int side;  // -1 entirely left of the tile, +1 entirely right, 0 crossing
-};
-Z2D_D EdgeClass classify(const double4& ev, double xl, double xr) {
-  EdgeClass c;
-  c.down = ev.x < ev.y;
-  c.top = c.down ? ev.x : ev.y;
-  c.bottom = c.down ? ev.y : ev.x;
-  // x along the edge is monotone between x_start and its value at the bottom; rounding moves it by <= 0.5
-  const double xe = ev.z + ev.w * (c.bottom - c.top);
-  const double xmin = ev.z < xe ? ev.z : xe, xmax = ev.z < xe ? xe : ev.z;
-  c.side = (xmin > xr) ? 1 : ((xmax < xl) ? -1 : 0);
-  return c;
-}
+// header helpers: {xlo, xhi, first active row | dir << 31, last active row} (k_bin_scatter)
+Z2D_D bool hdr_active(const int4& h, int ys) { return ys >= (h.z & 0x7fffffff) && ys <= h.w; }  // == top < ys + 0.5 <= bottom
 
-template <int W>
-Z2D_D void cross_pass(const DevEdge* __restrict__ be, uint32_t n_be, double ym0, double ym1, bool two, double xl, double xr, int sx0,
+template <int W, bool TWO>
+Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, uint64_t cross_bits, int ys0, int sx0,
                       int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1) {
-  uint64_t p0[W], p1[W];
+  uint64_t p0[W], p1[TWO ? W : 1];
 #pragma unroll
   for (int k = 0; k < W; k++) {  // start from the backdrop winding (two's complement, bit-sliced)
     p0[k] = ((wl0 >> k) & 1) ? ~0ull : 0ull;
-    p1[k] = ((wl1 >> k) & 1) ? ~0ull : 0ull;
+    if (TWO) p1[k] = ((wl1 >> k) & 1) ? ~0ull : 0ull;
   }
-  for (uint32_t i = 0; i < n_be; i++) {
-    const double4 ev = ld_edge(be + i);
-    const EdgeClass c = classify(ev, xl, xr);
-    if (c.side != 0) continue;
-    const int c0 = edge_col(ev, c.top, c.bottom, ym0, sx0, ncols);
-    if (c0 >= 0) {
-      const uint64_t mask = ~0ull << c0;
-      if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, !c.down);
+  const int sx_hi = sx0 + ncols;
+  const bool use_bits = n_be <= 64;
+  uint32_t i = 0;
+  while (true) {
+    if (use_bits) {  // iterate the crossing edges found by the classification pass
+      if (!cross_bits) break;
+      i = (uint32_t)__ffsll((long long)cross_bits) - 1u;
+      cross_bits &= cross_bits - 1;
+    } else {
+      if (i >= n_be) break;
     }
-    if (two) {
-      const int c1 = edge_col(ev, c.top, c.bottom, ym1, sx0, ncols);
-      if (c1 >= 0) {
-        const uint64_t mask = ~0ull << c1;
-        if (even_odd) p1[0] ^= mask; else wind_add<W>(p1, mask, !c.down);
+    const int4 h = __ldg(hd + i);
+    if (use_bits || (h.x <= sx_hi && h.y >= sx0)) {
+      const double4 ev = ld_edge(be + i);
+      const bool up = h.z < 0;
+      const double top = up ? ev.y : ev.x;
+      if (hdr_active(h, ys0)) {
+        const int c0 = edge_col(ev, top, ys0, sx0, ncols);
+        if (c0 >= 0) {
+          const uint64_t mask = ~0ull << c0;
+          if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, up);
+        }
+      }
+      if (TWO && hdr_active(h, ys0 + 1)) {
+        const int c1 = edge_col(ev, top, ys0 + 1, sx0, ncols);
+        if (c1 >= 0) {
+          const uint64_t mask = ~0ull << c1;
+          if (even_odd) p1[0] ^= mask; else wind_add<TWO ? W : 1>(p1, mask, up);
+        }
       }
     }
+    if (!use_bits) i++;
   }
   if (even_odd) {
     m0 = p0[0];
-    m1 = p1[0];
+    if (TWO) m1 = p1[0];
   } else {
     uint64_t a = 0, b = 0;
 #pragma unroll
     for (int k = 0; k < W; k++) {
       a |= p0[k];
-      b |= p1[k];
+      if (TWO) b |= p1[k];
     }
     m0 = a;
-    m1 = b;
+    if (TWO) m1 = b;
   }
 }
 
 // rare: more than 60 edges of one draw cross one tile; 32 planes in local memory, one row at a time
-__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, uint32_t n_be, double ym, double xl, double xr, int sx0,
+__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys, int sx0,
                                                 int ncols, bool even_odd, int wl) {
   uint64_t p[32];
   for (int k = 0; k < 32; k++) p[k] = ((wl >> k) & 1) ? ~0ull : 0ull;
+  const int sx_hi = sx0 + ncols;
   for (uint32_t i = 0; i < n_be; i++) {
+    const int4 h = __ldg(hd + i);
+    if (h.x > sx_hi || h.y < sx0 || !hdr_active(h, ys)) continue;
     const double4 ev = ld_edge(be + i);
-    const EdgeClass c = classify(ev, xl, xr);
-    if (c.side != 0) continue;
-    const int col = edge_col(ev, c.top, c.bottom, ym, sx0, ncols);
+    const bool up = h.z < 0;
+    const int col = edge_col(ev, up ? ev.y : ev.x, ys, sx0, ncols);
     if (col < 0) continue;
     uint64_t cy = ~0ull << col;
     if (even_odd) {
       p[0] ^= cy;
-    } else if (!c.down) {
+    } else if (up) {
       for (int k = 0; k < 32 && cy; k++) { const uint64_t t = p[k] & cy; p[k] ^= cy; cy = t; }
     } else {
       for (int k = 0; k < 32 && cy; k++) { const uint64_t t = ~p[k] & cy; p[k] ^= cy; cy = t; }
@@ -194,23 +227,23 @@ __device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, 
 }
 
 // Inside-masks of this lane's sub-scanlines ys0 (and ys0+1 when `two`) for one draw in one tile.
-Z2D_D void tile_cover(const DevEdge* __restrict__ be, uint32_t n_be, int ys0, bool two, int sx0, int ncols, uint32_t rule, uint64_t& m0,
-                      uint64_t& m1) {
-  const double ym0 = (double)ys0 + 0.5, ym1 = (double)ys0 + 1.5;
-  const double xl = (double)sx0 - 1.0, xr = (double)(sx0 + ncols) + 1.0;
+Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys0, bool two, int sx0, int ncols,
+                      uint32_t rule, uint64_t& m0, uint64_t& m1) {
   const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
+  const int sx_hi = sx0 + ncols;
   int wl0 = 0, wl1 = 0;
   uint32_t ncross = 0;
-  for (uint32_t i = 0; i < n_be; i++) {  // pass 1: backdrop from the edges left of the tile, count the crossing ones
-    const double4 ev = ld_edge(be + i);
-    const EdgeClass c = classify(ev, xl, xr);
-    if (c.side > 0) continue;
-    if (c.side < 0) {
-      const int dir = c.down ? -1 : 1;
-      if (c.top < ym0 && ym0 <= c.bottom) wl0 += dir;
-      if (two && c.top < ym1 && ym1 <= c.bottom) wl1 += dir;
+  uint64_t cross_bits = 0;
+  for (uint32_t i = 0; i < n_be; i++) {  // pass 1: backdrop from the edges left of the tile, find the crossing ones
+    const int4 h = __ldg(hd + i);        // warp-uniform address
+    if (h.x > sx_hi) continue;           // entirely right of the tile
+    if (h.y < sx0) {                     // entirely left: only its winding matters
+      const int dir = h.z < 0 ? 1 : -1;
+      if (hdr_active(h, ys0)) wl0 += dir;
+      if (two && hdr_active(h, ys0 + 1)) wl1 += dir;
     } else {
       ncross++;  // warp-uniform
+      if (i < 64) cross_bits |= 1ull << i;
     }
   }
   if (ncross == 0) {
@@ -223,12 +256,15 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, uint32_t n_be, int ys0, bo
   const bool full1 = !even_odd && (wl1 > (int)ncross || -wl1 > (int)ncross);
   const int b0 = full0 ? 0 : wl0, b1 = full1 ? 0 : wl1;
   if (ncross <= 7) {
-    cross_pass<5>(be, n_be, ym0, ym1, two, xl, xr, sx0, ncols, even_odd, b0, b1, m0, m1);
+    if (two) cross_pass<5, true>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1);
+    else cross_pass<5, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1);
   } else if (ncross <= 60) {
-    cross_pass<8>(be, n_be, ym0, ym1, two, xl, xr, sx0, ncols, even_odd, b0, b1, m0, m1);
+    uint64_t dummy = 0;
+    cross_pass<8, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, 0, m0, dummy);
+    if (two) cross_pass<8, false>(be, hd, n_be, cross_bits, ys0 + 1, sx0, ncols, even_odd, b1, 0, m1, dummy);
   } else {
-    m0 = cross_row_wide(be, n_be, ym0, xl, xr, sx0, ncols, even_odd, b0);
-    m1 = two ? cross_row_wide(be, n_be, ym1, xl, xr, sx0, ncols, even_odd, b1) : 0ull;
+    m0 = cross_row_wide(be, hd, n_be, ys0, sx0, ncols, even_odd, b0);
+    m1 = two ? cross_row_wide(be, hd, n_be, ys0 + 1, sx0, ncols, even_odd, b1) : 0ull;
   }
   if (full0) m0 = ~0ull;
   if (full1) m1 = ~0ull;
@@ -239,7 +275,7 @@ Z2D_D uint32_t nibble_popc(uint32_t x) {  // per-nibble popcount (values 0..4 in
   return (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
 }
 
-__global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
+__global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A) {
   __shared__ uint32_t tile_px[kRasterThreads / 32][8 * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
@@ -272,6 +308,10 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
   uint32_t n_cov = 0;
   const size_t row_idx = (size_t)py * (size_t)S.w;
   const bool row_ok = py < S.h;
+  TileFmt tf;
+  tf.fmt = S.fmt;
+  tf.is32 = S.fmt <= Z2D_FMT_RGBA;
+  tf.f = fmt32_of(S.fmt);
 
   for (uint32_t base = lb; base < le; base += 32) {
     uint2 it = make_uint2(0, 0);
@@ -300,11 +340,12 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
         const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
         const uint32_t eb = A.band_off[bslot], ee = A.band_off[bslot + 1];
         const DevEdge* be = A.band_edges + eb;
+        const int4* hd = A.band_hdr + eb;
         const uint32_t nbe = ee - eb;
         uint64_t m0 = 0, m1 = 0;
         const int sx0 = tx * kTile * Sc;
         if (Sc == 4) {
-          tile_cover(be, nbe, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, m0, m1);
           // pixel row `row` needs sub-scanlines 4*row .. 4*row+3: this lane's two and its partner's two
           const uint64_t q0 = __shfl_xor_sync(0xffffffffu, m0, 1), q1 = __shfl_xor_sync(0xffffffffu, m1, 1);
           const int sh = half * 32;
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
           cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
-          tile_cover(be, nbe, ty * kTile + row, false, sx0, 16, h.rule, m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile + row, false, sx0, 16, h.rule, m0, m1);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
             cov_e |= ((bits >> i) & 1u) << (4 * i);  // byte i/2
@@ -335,6 +376,7 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
 
       // ---- composite the lane's 8 pixels
       const DevDraw& d = A.draws[di];
+      const RGBA16 spx = unpack_rgba(h.px_rgba);
       for (int i = 0; i < 8; i++) {
         const int x = px0 + i;
         const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
@@ -349,7 +391,7 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster_tiles(RasterArgs A) {
         }
         if (in_reg) {
           n_cov += cov > 0;
-          raw = composite_cov(h, d, A.T, S.fmt, raw, cov, x, py);
+          raw = composite_cov(h, d, A.T, tf, spx, raw, cov, x, py);
         }
         px[i * 32 + lane] = raw;
       }

@@ -168,7 +168,9 @@ Z2D_HD bool op_is_bounded(uint32_t op) {
   return !(op == Z2D_OP_SRC_IN || op == Z2D_OP_DST_IN || op == Z2D_OP_SRC_OUT || op == Z2D_OP_DST_ATOP);
 }
 
-Z2D_HD int iM(int a, int b) { return a * b / 255; }       // mul, truncating (compositor.zig:1518-1523)
+// mul, truncating (compositor.zig:1518-1523).  Operands are channel values / 255 +- alpha, never negative,
+// so the unsigned form (mul.hi + shift instead of a signed division sequence) is exact.
+Z2D_HD int iM(int a, int b) { return (int)((unsigned)(a * b) / 255u); }
 Z2D_HD int iIM(int a, int b) { return iM(a, 255 - b); }   // invMul
 Z2D_HD int iRM(int a, int b) { return iM(a, 255 + b); }   // rInvMul
 Z2D_HD int imin(int a, int b) { return a < b ? a : b; }

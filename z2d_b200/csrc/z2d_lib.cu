@@ -113,7 +113,7 @@ struct z2d_ctx {
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
   DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
   uint32_t* h_total = nullptr;  // pinned readback slot
-  DevBuf d_counters, d_boxes, d_hots;
+  DevBuf d_counters, d_boxes, d_hots, d_band_hdr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   BatchMeta last;
   bool stats_pending = false;
@@ -388,8 +388,9 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     if (rc) return rc;
   }
   CK(c, c->d_band_edges.ensure((size_t)n_band_edges * sizeof(DevEdge) + 32));
+  CK(c, c->d_band_hdr.ensure((size_t)n_band_edges * sizeof(int4) + 32));
   launch_bin_scatter(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_off.as<uint32_t>(),
-                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), st);
+                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), c->d_band_hdr.as<int4>(), st);
   CK(c, cudaEventRecord(c->ev[2], st));
 
   // K3b: ordered draw list per surface tile-row
@@ -419,6 +420,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.hots = c->d_hots.as<DrawHot>();
   A.band_off = c->d_band_off.as<uint32_t>();
   A.band_edges = c->d_band_edges.as<DevEdge>();
+  A.band_hdr = c->d_band_hdr.as<int4>();
   A.counters = c->d_counters.as<unsigned long long>();
   A.T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
   launch_raster(A, st);
@@ -629,6 +631,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   if (c->h_total) cudaFreeHost(c->h_total);
   c->d_counters.release();
   c->d_boxes.release();
+  c->d_band_hdr.release();
   c->d_hots.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
