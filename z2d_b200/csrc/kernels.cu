@@ -230,8 +230,13 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
   }
 }
 
+}  // namespace z2d
+#include "stroke.cuh"
+namespace z2d {
+
 __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
-                                DevDraw* __restrict__ draws, uint32_t* __restrict__ sp_count) {
+                                DevDraw* __restrict__ draws, uint32_t* __restrict__ sp_count, const PenV* __restrict__ pens,
+                                const double* __restrict__ dashes) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
   const DevSubPath sp = sps[i];
@@ -239,6 +244,7 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
   EdgeSink<false> sink;
   sink.scale = d.scale;
   if (d.kind == 0) fill_subpath<false>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
+  else stroke_subpath<false>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
   sp_count[i] = sink.n;
   if (sink.n > 0) {
     atomicMin(&d.ext[0], f64_order(sink.top));
@@ -251,7 +257,8 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
 
 __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
                                const DevDraw* __restrict__ draws, const uint32_t* __restrict__ sp_off,
-                               DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw) {
+                               DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw, const PenV* __restrict__ pens,
+                               const double* __restrict__ dashes) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
   const DevSubPath sp = sps[i];
@@ -262,6 +269,7 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
   sink.out_draw = edge_draw + sp_off[i];
   sink.draw = sp.draw;
   if (d.kind == 0) fill_subpath<true>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
+  else stroke_subpath<true>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
 }
 
 // =====================================================================================
@@ -628,12 +636,13 @@ __global__ void k_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t ra
 // ------------------------------------------------------------------------- launchers
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
-void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, cudaStream_t st) {
-  if (n_sp) k_flatten_count<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_count);
+void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
+                          const double* dashes, cudaStream_t st) {
+  if (n_sp) k_flatten_count<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes);
 }
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
-                         DevEdge* edges, uint32_t* edge_draw, cudaStream_t st) {
-  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw);
+                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st) {
+  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes);
 }
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {
   if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, boxes, counters);

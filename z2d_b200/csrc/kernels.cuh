@@ -44,9 +44,11 @@ size_t scan_tmp_len(uint32_t n);
 // out[0..n) = exclusive scan of in[0..n), out[n] = total
 void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
 
-void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, cudaStream_t st);
+// pens: array of 6-double pen vertices {px,py,cw.dx,cw.dy,ccw.dx,ccw.dy} (tess/Pen.zig), dashes: concatenated dash arrays
+void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
+                          const double* dashes, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
-                         DevEdge* edges, uint32_t* edge_draw, cudaStream_t st);
+                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st);
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st);
 void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st);
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st);

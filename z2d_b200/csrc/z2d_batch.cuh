@@ -50,7 +50,7 @@ struct DevDraw {
   // stroke parameters (painter.zig:287-304 already applied)
   uint32_t cap, join;
   double thickness, miter_limit, dash_offset;
-  double ctm[6];
+  double ctm[6], inv[6];  // CTM and its inverse (Transformation.inverse, computed on the host)
   uint32_t dash_begin, dash_count;
   uint32_t pen_begin, pen_count;
   // --- produced on the device

@@ -106,8 +106,14 @@ struct z2d_ctx {
   std::vector<DevGrad> grads;
   std::vector<float> stop_offsets;
   std::vector<float4> stop_colors;
+  std::vector<double> dashes;   // concatenated dash arrays of the batch's dashed strokes
+  std::vector<double> pens;     // pen vertices, 6 doubles each {px,py,cw.dx,cw.dy,ccw.dx,ccw.dy}
+  double pen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // parameters of the most recently built pen (thickness, tolerance, ctm)
+  uint32_t pen_last_begin = 0, pen_last_count = 0;
+  bool pen_cached = false;
 
   // device state
+  DevBuf d_pens, d_dashes;
   DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -290,6 +296,91 @@ int pattern_to_src(const z2d_pattern& p, DevSrc& s, std::vector<DevGrad>& grads,
   }
 }
 
+
+// Transformation.inverse (Transformation.zig:103-162); the caller has already checked invertibility
+void invert_ctm(const double* m, double* o) {
+  const double ax = m[0], by = m[1], cx = m[2], dy = m[3], tx = m[4], ty = m[5];
+  if (by == 0 && cx == 0) {
+    if (ax != 1 || dy != 1) {
+      o[0] = 1 / ax; o[1] = 0; o[2] = 0; o[3] = 1 / dy; o[4] = -tx / ax; o[5] = -ty / dy;
+    } else {
+      o[0] = 1; o[1] = 0; o[2] = 0; o[3] = 1; o[4] = -tx; o[5] = -ty;
+    }
+    return;
+  }
+  const double det = ax * dy - by * cx;
+  const double k = 1 / det;
+  o[0] = dy * k; o[1] = -by * k; o[2] = -cx * k; o[3] = ax * k;
+  o[4] = (by * ty - dy * tx) * k;
+  o[5] = (cx * tx - ax * ty) * k;
+}
+
+// arc.transformed_circle_major_axis (internal/arc.zig:92-267)
+double major_axis(const double* m, double radius) {
+  const double eps = 0.00390625;
+  const double det = m[0] * m[3] - m[1] * m[2];
+  if (std::fabs(det * det - 1.0) < eps) {
+    if (std::fabs(m[1]) < eps && std::fabs(m[2]) < eps) return radius;
+    if (std::fabs(m[0]) < eps && std::fabs(m[3]) < eps) return radius;
+  }
+  const double i = m[0] * m[0] + m[1] * m[1], j = m[2] * m[2] + m[3] * m[3];
+  const double f = 0.5 * (i + j), g = 0.5 * (i - j), h = m[0] * m[2] + m[1] * m[3];
+  return radius * std::sqrt(f + std::hypot(g, h));
+}
+
+// Pen.init (tess/Pen.zig:36-129).  Built on the host with the C library's acos/cos/sin (the values the CPU
+// path uses) once per distinct (thickness, tolerance, CTM); the device only looks vertices up.
+void add_pen(z2d_ctx* c, DevDraw& d) {
+  const double key[8] = {d.thickness, d.tolerance, d.ctm[0], d.ctm[1], d.ctm[2], d.ctm[3], d.ctm[4], d.ctm[5]};
+  if (c->pen_cached && memcmp(key, c->pen_key, sizeof key) == 0) {
+    d.pen_begin = c->pen_last_begin;
+    d.pen_count = c->pen_last_count;
+    return;
+  }
+  const double radius = d.thickness / 2, tol = d.tolerance;
+  int n;
+  const double major = major_axis(d.ctm, radius);
+  if (tol >= major * 4) {
+    n = 1;
+  } else if (tol >= major) {
+    n = 4;
+  } else {
+    const double delta = std::acos(1 - tol / major);
+    if (delta == 0) {
+      n = 4;
+    } else {
+      n = (int)std::ceil(2 * M_PI / delta);
+      if (n < 4) n = 4;
+      else if (n % 2 != 0) n = n + 1;
+    }
+  }
+  const bool reflect = (d.ctm[0] * d.ctm[3] - d.ctm[1] * d.ctm[2]) < 0;
+  const size_t base = c->pens.size();
+  c->pens.resize(base + (size_t)n * 6);
+  double* v = c->pens.data() + base;
+  for (int i = 0; i < n; i++) {
+    double t = 2 * M_PI * (double)i / (double)n;
+    if (reflect) t = -t;
+    const double dx = radius * std::cos(t), dy = radius * std::sin(t);
+    v[i * 6 + 0] = d.ctm[0] * dx + d.ctm[1] * dy;
+    v[i * 6 + 1] = d.ctm[2] * dx + d.ctm[3] * dy;
+  }
+  for (int i = 0; i < n; i++) {
+    const int next = (i >= n - 1) ? 0 : i + 1;
+    const int prev = std::max(0, i == 0 ? n - 1 : i - 1);
+    v[i * 6 + 2] = v[i * 6 + 0] - v[prev * 6 + 0];  // slope_cw = Slope.init(prev, this)
+    v[i * 6 + 3] = v[i * 6 + 1] - v[prev * 6 + 1];
+    v[i * 6 + 4] = v[next * 6 + 0] - v[i * 6 + 0];  // slope_ccw = Slope.init(this, next)
+    v[i * 6 + 5] = v[next * 6 + 1] - v[i * 6 + 1];
+  }
+  d.pen_begin = (uint32_t)(base / 6);
+  d.pen_count = (uint32_t)n;
+  memcpy(c->pen_key, key, sizeof key);
+  c->pen_last_begin = d.pen_begin;
+  c->pen_last_count = d.pen_count;
+  c->pen_cached = true;
+}
+
 cudaError_t upload(z2d_ctx* c, DevBuf& b, const void* src, size_t bytes) {
   cudaError_t e = b.ensure(bytes ? bytes : 16);
   if (e != cudaSuccess) return e;
@@ -313,6 +404,9 @@ void clear_batch(z2d_ctx* c) {
   c->grads.clear();
   c->stop_offsets.clear();
   c->stop_colors.clear();
+  c->dashes.clear();
+  c->pens.clear();
+  c->pen_cached = false;
 }
 
 GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& sc) {
@@ -348,7 +442,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
   // K1: flatten (count, scan, emit)
   CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
-  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(), st);
+  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
+                       c->d_pens.p, c->d_dashes.as<double>(), st);
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_sp));
   uint32_t n_edges = 0;
   {
@@ -358,7 +453,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
   launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), st);
+                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
   CK(c, cudaEventRecord(c->ev[1], st));
 
   // K2: per-draw regions; (draw, tile-row) slots
@@ -500,6 +595,8 @@ int flush_impl(z2d_ctx* c) {
   CK(c, upload(c, c->d_grads, c->grads.data(), c->grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_stop_off, c->stop_offsets.data(), c->stop_offsets.size() * 4));
   CK(c, upload(c, c->d_stop_col, c->stop_colors.data(), c->stop_colors.size() * sizeof(float4)));
+  CK(c, upload(c, c->d_pens, c->pens.data(), c->pens.size() * 8));
+  CK(c, upload(c, c->d_dashes, c->dashes.data(), c->dashes.size() * 8));
   BatchMeta& m = c->last;
   m.valid = true;
   m.n_draws = n_draws;
@@ -623,7 +720,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   DevBuf* bufs[] = {&c->d_blue, &c->d_nodes, &c->d_subpaths, &c->d_draws, &c->d_sfcs, &c->d_grads, &c->d_stop_off, &c->d_stop_col,
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
-                    &c->d_scan_tmp, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col};
+                    &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col};
   for (DevBuf* b : bufs) b->release();
   c->nodes.release();
   c->subpaths.release();
@@ -848,8 +945,81 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
     }
   }
   if (n == 0) return Z2D_OK;
-  c->last_error = "stroke is not implemented on the device yet";
-  return Z2D_E_DEVICE;
+  if (o->op >= Z2D_OP_COUNT || o->precision > 1 || o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X || o->line_cap_mode > Z2D_CAP_SQUARE ||
+      o->line_join_mode > Z2D_JOIN_BEVEL || (o->n_dashes && !o->dashes))
+    return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (o->hairline) {
+    c->last_error = "hairline stroking is not implemented on the device yet";
+    return Z2D_E_DEVICE;
+  }
+  // Dasher.validate (tess/Dasher.zig:15-29): all >= 0 and at least one > 0, else the stroke is not dashed
+  bool dashed = false;
+  for (size_t i = 0; i < o->n_dashes; i++) {
+    if (o->dashes[i] < 0) {
+      dashed = false;
+      break;
+    }
+    if (o->dashes[i] > 0) dashed = true;
+  }
+  // plotter state machine errors (stroke_plotter.zig:113,134; dashed_plotter.zig:128,178,203): a line_to / curve_to
+  // (dashed: also close_path) without a current point fails the whole call with InvalidState
+  bool has_curve = false;
+  {
+    bool have_pt = false;
+    for (size_t i = 0; i < n; i++) {
+      switch (nodes[i].tag) {
+        case Z2D_NODE_MOVE_TO: have_pt = true; break;
+        case Z2D_NODE_CURVE_TO: has_curve = true;  // fallthrough
+        case Z2D_NODE_LINE_TO:
+          if (!have_pt) return Z2D_E_INVALID_STATE;
+          break;
+        case Z2D_NODE_CLOSE_PATH:
+          if (dashed && !have_pt) return Z2D_E_INVALID_STATE;
+          have_pt = false;
+          break;
+        default: return Z2D_E_INVALID_ARG;
+      }
+    }
+  }
+  DevDraw d;
+  memset(&d, 0, sizeof d);
+  d.kind = 1;
+  uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;  // painter.zig:240-243
+  if (aa == Z2D_AA_DEFAULT) aa = Z2D_AA_MULTISAMPLE_4X;
+  d.aa = aa;
+  d.rule = Z2D_FILL_NON_ZERO;  // painter.zig:308-343
+  d.op = o->op;
+  d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
+  d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
+  d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {
+    c->last_error = "unbounded operator without anti-aliasing is not implemented on the device yet";
+    return Z2D_E_DEVICE;
+  }
+  // painter.zig:287-304: thin lines lose cap / join / miter settings; minimum width 1/256
+  const double min_w = 0.00390625;
+  d.cap = o->line_width >= 2 ? o->line_cap_mode : (uint32_t)Z2D_CAP_BUTT;
+  d.join = o->line_width >= 2 ? o->line_join_mode : (uint32_t)Z2D_JOIN_MITER;
+  d.miter_limit = o->line_width >= 2 ? o->miter_limit : 10.0;
+  d.thickness = o->line_width >= min_w ? o->line_width : min_w;
+  d.dash_offset = o->dash_offset;
+  for (int i = 0; i < 6; i++) d.ctm[i] = o->ctm[i];
+  invert_ctm(o->ctm, d.inv);
+  const size_t save_d = c->dashes.size(), save_p = c->pens.size();
+  if (dashed) {
+    d.dash_begin = (uint32_t)c->dashes.size();
+    d.dash_count = (uint32_t)o->n_dashes;
+    c->dashes.insert(c->dashes.end(), o->dashes, o->dashes + o->n_dashes);
+  }
+  // the pen exists when a round join / cap is requested, or lazily once a curve is stroked (stroke_plotter.zig:56-59,139-144)
+  if (d.join == Z2D_JOIN_ROUND || d.cap == Z2D_CAP_ROUND || has_curve) add_pen(c, d);
+  int32_t rc = record_draw(c, s, pattern, nodes, n, d);
+  if (rc != Z2D_OK && rc != Z2D_E_DEVICE) {
+    c->dashes.resize(std::min(save_d, c->dashes.size()));
+    c->pens.resize(std::min(save_p, c->pens.size()));
+  }
+  return rc;
 }
 
 int32_t z2d_submit(z2d_ctx* c, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses) {

@@ -795,6 +795,21 @@ class Context:
     def set_source_to_pixel(self, px):
         self.pattern = Pattern.opaque(px)
 
+    def get_source(self):
+        return self.pattern
+
+    def get_transformation(self):
+        return self.transformation
+
+    def get_line_width(self):
+        return self.line_width
+
+    def device_to_user_distance(self, x, y):
+        return self.transformation.device_to_user_distance(x, y)
+
+    def user_to_device_distance(self, x, y):
+        return self.transformation.user_to_device_distance(x, y)
+
     def set_dither(self, d):
         self.dither = DitherType(d)
 
