@@ -44,3 +44,32 @@ def test_compositor_scene(cuda, oracle, stem):
     got = specs.COMPOSITOR_SCENES[stem](specs.bind(cuda))
     ref = specs.COMPOSITOR_SCENES[stem](specs.bind(oracle))
     _compare(stem, got, ref)
+
+
+# --- the device output against the reference's own golden images (committed fixtures) -------------------
+# 044: host-libm sensitive (see tests/test_oracle_goldens.py); demultiplied / sRGB-encoded exports of float
+# scenes may amplify a 1-LSB difference, so those get a small per-channel tolerance instead of equality.
+GOLDEN_PIXEL_BUDGET = {"044_line_transforms": 150}
+
+
+@pytest.mark.parametrize("stem,aa", PATH_CASES, ids=[f"{s}-{a.name}" for s, a in PATH_CASES])
+def test_path_scene_matches_reference_golden(cuda, stem, aa):
+    sfc = specs.PATH_SCENES[stem](specs.bind(cuda), aa)
+    n, got, exp = golden_util.diff_count(sfc, golden_util.golden_path(stem, aa), specs.COLOR_PROFILE.get(stem))
+    assert n >= 0, f"{stem}: shape differs from the golden"
+    if stem in FLOAT_SCENES:
+        worst = int(np.abs(got.astype(np.int32) - exp.astype(np.int32)).max())
+        assert worst <= 2, f"{stem} {aa.name}: max exported channel difference {worst}"
+    else:
+        assert n <= GOLDEN_PIXEL_BUDGET.get(stem, 0), f"{stem} {aa.name}: {n} pixels differ from the reference golden"
+
+
+@pytest.mark.parametrize("stem", sorted(specs.COMPOSITOR_SCENES))
+def test_compositor_scene_matches_reference_golden(cuda, stem):
+    sfc = specs.COMPOSITOR_SCENES[stem](specs.bind(cuda))
+    n, got, exp = golden_util.diff_count(sfc, golden_util.golden_path(stem), specs.COLOR_PROFILE.get(stem))
+    assert n >= 0
+    if stem in FLOAT_SCENES:
+        assert int(np.abs(got.astype(np.int32) - exp.astype(np.int32)).max()) <= 2
+    else:
+        assert n == 0, f"{stem}: {n} pixels differ from the reference golden"

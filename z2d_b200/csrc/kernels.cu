@@ -132,6 +132,7 @@ Z2D_D Knots knots_split(Knots& k) {  // tess/Spline.zig:128-151 (k becomes the f
 // Edge sink: applies Polygon.addEdge (tess/Polygon.zig:61-109).  EMIT=false counts and tracks extents.
 template <bool EMIT>
 struct EdgeSink {
+  bool unpaired = false;
   double scale;
   uint32_t n = 0;
   double top, bottom, left, right;
@@ -225,6 +226,8 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
           if (pt_eq(last, first)) break;
           sink.add(last, first);
           add_pt(first);
+        } else if (len == 2) {
+          sink.unpaired = true;  // a lone edge that is never closed: rows crossing it have an unpaired crossing
         }
     }
   }
@@ -246,6 +249,7 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
   if (d.kind == 0) fill_subpath<false>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
   else stroke_subpath<false>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
   sp_count[i] = sink.n;
+  if (sink.unpaired && sink.n > 0) atomicOr(&d.flags, kDrawUnpaired);
   if (sink.n > 0) {
     atomicMin(&d.ext[0], f64_order(sink.top));
     atomicMax(&d.ext[1], f64_order(sink.bottom));
@@ -287,6 +291,7 @@ __global__ void k_reset_draws(DevDraw* __restrict__ draws, uint32_t n_draws) {  
   d.ext[3] = f64_order(-INFINITY);
   d.n_edges = 0;
   d.valid = 0;
+  d.flags = 0;
 }
 
 __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
@@ -366,6 +371,7 @@ __global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws
   h.ey0 = d.ey0; h.ey1 = d.ey1;
   h.band_base = d.band_base; h.unbounded = d.unbounded;
   h.pre_y0 = d.pre_y0; h.pre_y1 = d.pre_y1; h.pre_x = d.pre_x; h.pre_rows = d.pre_rows;
+  h.flags = d.flags; h._pad[0] = h._pad[1] = h._pad[2] = 0;
   hots[i] = h;
 }
 
@@ -635,6 +641,20 @@ __global__ void k_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t ra
 
 // ------------------------------------------------------------------------- launchers
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace z2d
+#include "slowpath.cuh"
+namespace z2d {
+
+void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const z2d_node* nodes, uint32_t node_begin,
+                     uint32_t node_end, const double* dashes, const GradTables& T, cudaStream_t st) {
+  k_hairline<<<1, 32, 0, st>>>(sfcs, draws, draw_index, nodes, node_begin, node_end, dashes, T);
+}
+void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const DevEdge* edges, uint32_t n_edges,
+                             int rows, const GradTables& T, cudaStream_t st) {
+  if (rows <= 0) return;
+  k_direct_unbounded<<<(rows + 63) / 64, 64, 0, st>>>(sfcs, draws, draw_index, edges, n_edges, T);
+}
 
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
                           const double* dashes, cudaStream_t st) {

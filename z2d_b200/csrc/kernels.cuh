@@ -58,6 +58,11 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
                        const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
 void launch_raster(const RasterArgs& A, cudaStream_t st);
+// isolated single-draw modes (slowpath.cuh)
+void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const z2d_node* nodes, uint32_t node_begin,
+                     uint32_t node_end, const double* dashes, const GradTables& T, cudaStream_t st);
+void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const DevEdge* edges, uint32_t n_edges,
+                             int rows, const GradTables& T, cudaStream_t st);
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st);
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st);
 void launch_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t raw, cudaStream_t st);

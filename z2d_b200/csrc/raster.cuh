@@ -270,6 +270,47 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
   if (full1) m1 = ~0ull;
 }
 
+// Draws flagged kDrawUnpaired only.  The reference pairs the sorted (filtered) crossings of a scanline and drops a
+// trailing unmatched one ("for (0..filtered_edge_set.len / 2)", multisample.zig / supersample.zig / direct.zig), so
+// the inside run that would extend to +infinity is not drawn: clear every sample at or right of the crossing that
+// opens it.  even-odd: the largest crossing; non-zero: the largest crossing with zero winding left of it.
+__device__ __noinline__ uint64_t drop_open_tail(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys, int sx0,
+                                                int ncols, bool even_odd, uint64_t m) {
+  int total = 0, n = 0;
+  for (uint32_t i = 0; i < n_be; i++) {
+    const int4 h = __ldg(hd + i);
+    if (!hdr_active(h, ys)) continue;
+    total += h.z < 0 ? 1 : -1;
+    n++;
+  }
+  if (even_odd ? !(n & 1) : total == 0) return m;
+  const double mid = (double)ys + 0.5;
+  double x_cut = -INFINITY;
+  for (uint32_t j = 0; j < n_be; j++) {
+    const int4 hj = __ldg(hd + j);
+    if (!hdr_active(hj, ys)) continue;
+    const double4 ej = ld_edge(be + j);
+    const double xj = round_half_away(ej.z + (ej.w * (mid - (hj.z < 0 ? ej.y : ej.x))));
+    if (!(xj > x_cut)) continue;
+    if (!even_odd) {
+      int before = 0;
+      for (uint32_t i = 0; i < n_be; i++) {
+        const int4 hi = __ldg(hd + i);
+        if (!hdr_active(hi, ys)) continue;
+        const double4 ei = ld_edge(be + i);
+        const double xi = round_half_away(ei.z + (ei.w * (mid - (hi.z < 0 ? ei.y : ei.x))));
+        if (xi < xj) before += hi.z < 0 ? 1 : -1;
+      }
+      if (before != 0) continue;
+    }
+    x_cut = xj;
+  }
+  const double cf = x_cut - (double)sx0;
+  if (!(cf < (double)ncols)) return m;
+  if (cf <= 0.0) return 0ull;
+  return m & ~(~0ull << (int)cf);
+}
+
 Z2D_D uint32_t nibble_popc(uint32_t x) {  // per-nibble popcount (values 0..4 in each 4-bit field)
   x = x - ((x >> 1) & 0x55555555u);
   return (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
@@ -346,6 +387,10 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
         const int sx0 = tx * kTile * Sc;
         if (Sc == 4) {
           tile_cover(be, hd, nbe, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, m0, m1);
+          if (h.flags & kDrawUnpaired) {
+            m0 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m0);
+            m1 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2 + 1, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m1);
+          }
           // pixel row `row` needs sub-scanlines 4*row .. 4*row+3: this lane's two and its partner's two
           const uint64_t q0 = __shfl_xor_sync(0xffffffffu, m0, 1), q1 = __shfl_xor_sync(0xffffffffu, m1, 1);
           const int sh = half * 32;
@@ -355,6 +400,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
           tile_cover(be, hd, nbe, ty * kTile + row, false, sx0, 16, h.rule, m0, m1);
+          if (h.flags & kDrawUnpaired) m0 = drop_open_tail(be, hd, nbe, ty * kTile + row, sx0, 16, h.rule == Z2D_FILL_EVEN_ODD, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
             cov_e |= ((bits >> i) & 1u) << (4 * i);  // byte i/2

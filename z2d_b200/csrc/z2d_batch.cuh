@@ -53,7 +53,14 @@ struct DevDraw {
   double ctm[6], inv[6];  // CTM and its inverse (Transformation.inverse, computed on the host)
   uint32_t dash_begin, dash_count;
   uint32_t pen_begin, pen_count;
+  // isolated modes (slowpath.cuh): 0 tile pipeline, 1 hairline, 2 direct rasteriser with an unbounded operator
+  uint32_t mode;
+  uint32_t hair_aa;            // hairline: the caller's AA mode (none => Bresenham, else Wu)
+  double hair_tolerance;       // hairline: untouched opts.tolerance (painter.zig:262-277)
+  uint32_t node_begin, node_end;  // hairline: the whole node list of the draw
   // --- produced on the device
+  uint32_t flags;      // kDrawUnpaired: some sub-path left a dangling edge (fill_plotter.zig:78-97 with 2 points)
+  uint32_t _pad0;
   long long ext[4];    // order-encoded f64: top(min) bottom(max) left(min) right(max)
   uint32_t n_edges;
   uint32_t valid;
@@ -64,6 +71,8 @@ struct DevDraw {
   uint32_t band_base;           // first (draw, tile-row) slot
   uint32_t unbounded;
 };
+
+constexpr uint32_t kDrawUnpaired = 1u;
 
 struct DevEdge {
   double y0, y1, x_start, x_inc;
@@ -82,6 +91,7 @@ struct DrawHot {
   int32_t ey0, ey1;
   uint32_t band_base, unbounded;
   int32_t pre_y0, pre_y1, pre_x, pre_rows;
+  uint32_t flags, _pad[3];
 };
 
 // order-preserving f64 <-> i64 (for atomicMin / atomicMax on extents)

@@ -537,6 +537,53 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   return Z2D_OK;
 }
 
+// Hairline strokes and the direct rasteriser with an unbounded operator are order / row-globally coupled
+// (slowpath.cuh); they run as a batch of exactly one draw.
+int run_isolated(z2d_ctx* c) {
+  const BatchMeta& m = c->last;
+  cudaStream_t st = c->stream;
+  const DevDraw& hd = c->draws.p[0];
+  const GradTables T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
+  uint32_t launches = 0, n_edges = 0;
+  CK(c, cudaEventRecord(c->ev[0], st));
+  if (hd.mode == 1) {
+    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), hd.node_begin, hd.node_end,
+                    c->d_dashes.as<double>(), T, st);
+    launches = 1;
+  } else {
+    const uint32_t n_sp = m.n_sp;
+    CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
+    launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
+                         c->d_pens.p, c->d_dashes.as<double>(), st);
+    CK(c, c->d_sp_off.ensure(((size_t)n_sp + 1) * 4));
+    CK(c, c->d_scan_tmp.ensure(scan_tmp_len(n_sp) * 4));
+    exclusive_scan(c->d_sp_count.as<uint32_t>(), c->d_sp_off.as<uint32_t>(), n_sp, c->d_scan_tmp.as<uint32_t>(), st);
+    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
+    if (rc) return rc;
+    CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
+    CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
+    launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
+                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
+    launch_direct_unbounded(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, c->batch_sfcs[0]->h, T, st);
+    launches = 6;
+  }
+  CK(c, cudaGetLastError());
+  for (int i = 1; i <= 4; i++) CK(c, cudaEventRecord(c->ev[i], st));
+  // the pinned batch arrays are reused by the next draw: their async uploads must have landed (the tile
+  // pipeline gets this from its read-backs)
+  CK(c, cudaStreamSynchronize(st));
+  z2d_stats& s = c->stats;
+  memset(&s, 0, sizeof s);
+  s.draws = 1;
+  s.nodes = m.n_nodes;
+  s.edges = n_edges;
+  s.kernel_launches = launches;
+  s.h2d_bytes = m.h2d_bytes;
+  c->stats_pending = true;
+  c->last.valid = false;  // not replayable
+  return Z2D_OK;
+}
+
 int flush_impl(z2d_ctx* c) {
   const uint32_t n_draws = (uint32_t)c->draws.n;
   if (n_draws == 0) {
@@ -608,7 +655,7 @@ int flush_impl(z2d_ctx* c) {
   m.h2d_bytes = c->nodes.n * sizeof(z2d_node) + c->subpaths.n * sizeof(DevSubPath) + c->draws.n * sizeof(DevDraw) +
                 sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + c->grads.size() * sizeof(DevGrad) +
                 c->stop_offsets.size() * 4 + c->stop_colors.size() * sizeof(float4);
-  int rc = run_pipeline(c, false);
+  int rc = (n_draws == 1 && c->draws.p[0].mode != 0) ? run_isolated(c) : run_pipeline(c, false);
   clear_batch(c);
   return rc;
 }
@@ -894,6 +941,8 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   const size_t save_nodes = c->nodes.n, save_sp = c->subpaths.n;
   const uint32_t di = (uint32_t)c->draws.n;
   rc = record_nodes(c, di, nodes, n);
+  d.node_begin = (uint32_t)save_nodes;
+  d.node_end = (uint32_t)c->nodes.n;
   if (rc == Z2D_OK && !c->draws.push(d)) rc = Z2D_E_OUT_OF_MEMORY;
   if (rc) {  // roll back: the failed call draws nothing
     c->nodes.n = save_nodes;
@@ -903,7 +952,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     c->stop_colors.resize(save_c);
     return rc;
   }
-  if (c->nodes.n > kMaxBatchNodes || c->draws.n > kMaxBatchDraws) return flush(c);
+  if (d.mode != 0 || c->nodes.n > kMaxBatchNodes || c->draws.n > kMaxBatchDraws) return flush(c);
   return Z2D_OK;
 }
 
@@ -926,9 +975,10 @@ int32_t z2d_fill(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_n
   d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;  // multisample.zig:36, compositor.zig:317-322
   d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
   d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;  // painter.zig:103
-  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {
-    c->last_error = "unbounded operator without anti-aliasing is not implemented on the device yet";
-    return Z2D_E_DEVICE;
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {  // direct.zig clears per span pair: row-global, runs isolated
+    d.mode = 2;
+    int frc = flush(c);  // everything recorded so far lands first
+    if (frc) return frc;
   }
   return record_draw(c, s, pattern, nodes, n, d);
 }
@@ -949,10 +999,6 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
       o->line_join_mode > Z2D_JOIN_BEVEL || (o->n_dashes && !o->dashes))
     return Z2D_E_INVALID_ARG;
   cudaSetDevice(c->device);
-  if (o->hairline) {
-    c->last_error = "hairline stroking is not implemented on the device yet";
-    return Z2D_E_DEVICE;
-  }
   // Dasher.validate (tess/Dasher.zig:15-29): all >= 0 and at least one > 0, else the stroke is not dashed
   bool dashed = false;
   for (size_t i = 0; i < o->n_dashes; i++) {
@@ -961,6 +1007,34 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
       break;
     }
     if (o->dashes[i] > 0) dashed = true;
+  }
+  if (o->hairline) {  // painter.zig:246-265: polyline plotter + hairline rasteriser, AA mode and tolerance as given
+    bool have_pt = false;
+    for (size_t i = 0; i < n; i++) {  // polyline_plotter.zig:62-85: line_to / curve_to before any move_to
+      if (nodes[i].tag == Z2D_NODE_MOVE_TO) have_pt = true;
+      else if (nodes[i].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+      else if (nodes[i].tag != Z2D_NODE_CLOSE_PATH && !have_pt) return Z2D_E_INVALID_STATE;
+    }
+    DevDraw d;
+    memset(&d, 0, sizeof d);
+    d.kind = 1;
+    d.mode = 1;
+    d.op = o->op;
+    d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
+    d.hair_aa = o->anti_aliasing_mode;
+    d.hair_tolerance = o->tolerance;
+    d.dash_offset = o->dash_offset;
+    int frc = flush(c);  // isolated draw: everything recorded so far lands first
+    if (frc) return frc;
+    const size_t save_d = c->dashes.size();
+    if (dashed) {
+      d.dash_begin = (uint32_t)c->dashes.size();
+      d.dash_count = (uint32_t)o->n_dashes;
+      c->dashes.insert(c->dashes.end(), o->dashes, o->dashes + o->n_dashes);
+    }
+    int32_t rc = record_draw(c, s, pattern, nodes, n, d);
+    if (rc != Z2D_OK) c->dashes.resize(std::min(save_d, c->dashes.size()));
+    return rc;
   }
   // plotter state machine errors (stroke_plotter.zig:113,134; dashed_plotter.zig:128,178,203): a line_to / curve_to
   // (dashed: also close_path) without a current point fails the whole call with InvalidState
@@ -994,8 +1068,9 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
   d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;
   if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {
-    c->last_error = "unbounded operator without anti-aliasing is not implemented on the device yet";
-    return Z2D_E_DEVICE;
+    d.mode = 2;
+    int frc = flush(c);
+    if (frc) return frc;
   }
   // painter.zig:287-304: thin lines lose cap / join / miter settings; minimum width 1/256
   const double min_w = 0.00390625;
