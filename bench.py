@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from z2d_b200 import abi, workloads
+    from z2d_b200 import abi, sharding, workloads
     from z2d_b200.cuda_backend import CudaBackend
     from z2d_b200.host import Pixel, Surface
 
@@ -160,7 +160,7 @@ def run_ours(args, rank, world, local_rank):
     cb = CudaBackend(local_rank, stream=stream.cuda_stream)
     lib = cb.lib
 
-    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=0x7A326402 + rank)
+    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=sharding.scene_seed(sharding.BASE_SEED_C2, rank))
     sfc = Surface(abi.Format.rgba, args.size, args.size, None, cb)
     cmds = scene.draw_cmds(sfc.handle)
     cmds_p = cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD))
@@ -218,13 +218,8 @@ def run_ours(args, rank, world, local_rank):
         total_ms.append(s["ms_total"])
     st = cb.stats()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(st["covered_px"]), float(st["draws"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    covered_all, draws_all = float(cnt[0]), float(cnt[1])
+    (dev_ms, e2e_ms), (covered_all, draws_all) = sharding.reduce_timing(
+        [dev_ms, e2e_s * 1e3], [st["covered_px"], st["draws"]], device="cuda", dist=dist if world > 1 else None)
 
     # ---- compositor kernel roofline (config 4 shape: 8192^2 RGBA8 src_over, single-pixel source)
     comp = None
