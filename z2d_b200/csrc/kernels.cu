@@ -281,17 +281,45 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
 // =====================================================================================
 Z2D_D int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
 
-__global__ void k_reset_draws(DevDraw* __restrict__ draws, uint32_t n_draws) {  // replay: undo what the pipeline wrote
+// DrawIn (+ side tables) -> DevDraw; also (re)initialises everything the pipeline writes, so a replay starts clean
+__global__ void k_expand_draws(const DrawIn* __restrict__ in, const StrokeIn* __restrict__ strokes, const DevSrc* __restrict__ srcs,
+                               DevDraw* __restrict__ draws, uint32_t n_draws) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
-  DevDraw& d = draws[i];
+  const DrawIn q = in[i];
+  DevDraw d;
+  memset(&d, 0, sizeof d);
+  d.surface = q.surface;
+  d.kind = q.opts & 1u;
+  d.aa = (q.opts >> 1) & 3u;
+  d.rule = (q.opts >> 3) & 1u;
+  d.op = (q.opts >> 4) & 31u;
+  d.precision = (q.opts >> 9) & 1u;
+  d.reduces = (q.opts >> 10) & 1u;
+  d.mode = (q.opts >> 11) & 3u;
+  d.paint_raw = q.paint_raw;
+  d.scale = d.aa == Z2D_AA_NONE ? 1.0 : 4.0;
+  d.tolerance = q.tolerance;
+  if (q.src_index == kNoIndex) {
+    d.src.kind = Z2D_PARAM_PIXEL;
+    d.src.px_rgba = q.px_rgba;
+  } else {
+    d.src = srcs[q.src_index];
+  }
+  if (q.stroke_index != kNoIndex) {
+    const StrokeIn s = strokes[q.stroke_index];
+    d.cap = s.cap; d.join = s.join;
+    d.thickness = s.thickness; d.miter_limit = s.miter_limit; d.dash_offset = s.dash_offset;
+    for (int k = 0; k < 6; k++) { d.ctm[k] = s.ctm[k]; d.inv[k] = s.inv[k]; }
+    d.dash_begin = s.dash_begin; d.dash_count = s.dash_count;
+    d.pen_begin = s.pen_begin; d.pen_count = s.pen_count;
+    d.hair_aa = s.hair_aa; d.hair_tolerance = s.hair_tolerance;
+  }
   d.ext[0] = f64_order(INFINITY);
   d.ext[1] = f64_order(-INFINITY);
   d.ext[2] = f64_order(INFINITY);
   d.ext[3] = f64_order(-INFINITY);
-  d.n_edges = 0;
-  d.valid = 0;
-  d.flags = 0;
+  draws[i] = d;
 }
 
 __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
@@ -667,8 +695,8 @@ void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {
   if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, boxes, counters);
 }
-void launch_reset_draws(DevDraw* draws, uint32_t n, cudaStream_t st) {
-  if (n) k_reset_draws<<<blocks_for(n, 256), 256, 0, st>>>(draws, n);
+void launch_expand_draws(const DrawIn* in, const StrokeIn* strokes, const DevSrc* srcs, DevDraw* draws, uint32_t n, cudaStream_t st) {
+  if (n) k_expand_draws<<<(n + 127) / 128, 128, 0, st>>>(in, strokes, srcs, draws, n);
 }
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st) {
   if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off, hots);

@@ -162,18 +162,19 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
       if (i >= n_be) break;
     }
     const int4 h = __ldg(hd + i);
-    if (use_bits || (h.x <= sx_hi && h.y >= sx0)) {
+    const bool a0 = hdr_active(h, ys0), a1 = TWO && hdr_active(h, ys0 + 1);
+    if ((a0 || a1) && (use_bits || (h.x <= sx_hi && h.y >= sx0))) {
       const double4 ev = ld_edge(be + i);
       const bool up = h.z < 0;
       const double top = up ? ev.y : ev.x;
-      if (hdr_active(h, ys0)) {
+      if (a0) {
         const int c0 = edge_col(ev, top, ys0, sx0, ncols);
         if (c0 >= 0) {
           const uint64_t mask = ~0ull << c0;
           if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, up);
         }
       }
-      if (TWO && hdr_active(h, ys0 + 1)) {
+      if (TWO && a1) {
         const int c1 = edge_col(ev, top, ys0 + 1, sx0, ncols);
         if (c1 >= 0) {
           const uint64_t mask = ~0ull << c1;
@@ -226,26 +227,64 @@ __device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, 
   return a;
 }
 
-// Inside-masks of this lane's sub-scanlines ys0 (and ys0+1 when `two`) for one draw in one tile.
-Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys0, bool two, int sx0, int ncols,
-                      uint32_t rule, uint64_t& m0, uint64_t& m1) {
+// Inside-masks of this lane's sub-scanlines ys0 (and ys0+1 when `two`) for one draw in one tile.  Called by the whole warp
+// with warp-uniform be / hd / n_be; `wdiff` is the warp's 65-entry scratch in shared memory and ys_tile0 the tile's
+// first (sub-)scanline.
+Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, bool two, int sx0,
+                      int ncols, uint32_t rule, int* __restrict__ wdiff, uint64_t& m0, uint64_t& m1) {
   const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
+  const int lane = (int)(threadIdx.x & 31u);
   const int sx_hi = sx0 + ncols;
-  int wl0 = 0, wl1 = 0;
+  const int nrows = two ? 64 : 16;
+  // pass 1, lanes stride over the edges: an edge entirely left of the tile adds its direction to the backdrop winding of
+  // the rows it is active on (a +dir / -dir pair in a per-row difference array); crossing edges are collected in a bit mask
+  wdiff[lane] = 0;
+  wdiff[lane + 32] = 0;
+  if (lane == 0) wdiff[64] = 0;
+  __syncwarp();
   uint32_t ncross = 0;
   uint64_t cross_bits = 0;
-  for (uint32_t i = 0; i < n_be; i++) {  // pass 1: backdrop from the edges left of the tile, find the crossing ones
-    const int4 h = __ldg(hd + i);        // warp-uniform address
-    if (h.x > sx_hi) continue;           // entirely right of the tile
-    if (h.y < sx0) {                     // entirely left: only its winding matters
-      const int dir = h.z < 0 ? 1 : -1;
-      if (hdr_active(h, ys0)) wl0 += dir;
-      if (two && hdr_active(h, ys0 + 1)) wl1 += dir;
+  for (uint32_t base = 0; base < n_be; base += 32) {
+    const uint32_t i = base + (uint32_t)lane;
+    bool cross = false;
+    if (i < n_be) {
+      const int4 h = __ldg(hd + i);
+      if (h.x <= sx_hi) {      // else entirely right of the tile
+        if (h.y < sx0) {       // entirely left: only its winding matters
+          const int r0 = max((h.z & 0x7fffffff) - ys_tile0, 0), r1 = min(h.w - ys_tile0, nrows - 1);
+          if (r0 <= r1) {
+            const int dir = h.z < 0 ? 1 : -1;
+            atomicAdd(&wdiff[r0], dir);
+            atomicAdd(&wdiff[r1 + 1], -dir);
+          }
+        } else {
+          cross = true;
+        }
+      }
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, cross);
+    ncross += (uint32_t)__popc(b);
+    if (base < 64) cross_bits |= (uint64_t)b << base;
+  }
+  __syncwarp();
+  int wl0, wl1 = 0;
+  {  // prefix sum of the difference array -> backdrop winding of this lane's rows
+    const int a = two ? wdiff[2 * lane] : (lane < 16 ? wdiff[lane] : 0);
+    const int b = two ? wdiff[2 * lane + 1] : 0;
+    int incl = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (two) {
+      wl0 = incl - b;
+      wl1 = incl;
     } else {
-      ncross++;  // warp-uniform
-      if (i < 64) cross_bits |= 1ull << i;
+      wl0 = __shfl_sync(0xffffffffu, incl, lane >> 1);
     }
   }
+  __syncwarp();  // wdiff is rewritten by the next call
   if (ncross == 0) {
     m0 = (even_odd ? (wl0 & 1) : (wl0 != 0)) ? ~0ull : 0ull;
     m1 = (even_odd ? (wl1 & 1) : (wl1 != 0)) ? ~0ull : 0ull;
@@ -316,8 +355,33 @@ Z2D_D uint32_t nibble_popc(uint32_t x) {  // per-nibble popcount (values 0..4 in
   return (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
 }
 
+// ---- packed integer src_over for the 32-bit formats (two 16-bit lanes per register: bytes 0,2 and bytes 1,3;
+// alpha / padding is byte 3 in all four layouts).  floor(p / 255) == (p + 1 + (p >> 8)) >> 8 for 0 <= p <= 65534.
+Z2D_D uint32_t div255_x2(uint32_t p) { return ((p + 0x00010001u + ((p >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu; }
+// source pixel at mask m, in the surface's channel layout: mask_mul16 == dst_in(src, alpha8 m) (surface.zig:573-576)
+Z2D_D uint2 src_lanes(const Fmt32& f, RGBA16 s, int m, bool masked) {
+  const uint32_t c0 = f.rs == 0 ? (uint32_t)s.r : (uint32_t)s.b, c2 = f.rs == 0 ? (uint32_t)s.b : (uint32_t)s.r;
+  uint32_t lo = c0 | (c2 << 16), hi = (uint32_t)s.g | ((uint32_t)s.a << 16);
+  if (masked) {
+    lo = div255_x2(lo * (uint32_t)m);
+    hi = div255_x2(hi * (uint32_t)m);
+  }
+  return make_uint2(lo, hi);
+}
+// IntegerOps.src_over: colour = sc + dc * (255 - sa) / 255, alpha = sa + da - sa * da / 255  (compositor.zig:1216-1231)
+// The alpha lane uses sa * da / 255 == da - ceil(da * (255 - sa) / 255), i.e. sa + (da * inv + 254) / 255.
+Z2D_D uint32_t src_over_x4(uint32_t raw, uint2 s, uint32_t amask) {
+  const uint32_t inv = 255u - (s.y >> 16);
+  const uint32_t dlo = raw & 0x00ff00ffu, dhi = ((raw | ~amask) >> 8) & 0x00ff00ffu;  // no alpha channel: da = 255
+  const uint32_t lo = s.x + div255_x2(dlo * inv);
+  const uint32_t hi = s.y + div255_x2(dhi * inv + (254u << 16));
+  return (lo | (hi << 8)) & amask;
+}
+
 __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A) {
   __shared__ uint32_t tile_px[kRasterThreads / 32][8 * 32];
+  __shared__ uint2 src_tab[kRasterThreads / 32][17];
+  __shared__ int wdiff_s[kRasterThreads / 32][66];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
   if (gt >= A.n_tiles) return;
@@ -386,7 +450,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
         uint64_t m0 = 0, m1 = 0;
         const int sx0 = tx * kTile * Sc;
         if (Sc == 4) {
-          tile_cover(be, hd, nbe, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, wdiff_s[warp], m0, m1);
           if (h.flags & kDrawUnpaired) {
             m0 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m0);
             m1 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2 + 1, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m1);
@@ -399,7 +463,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
           cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
-          tile_cover(be, hd, nbe, ty * kTile + row, false, sx0, 16, h.rule, m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, wdiff_s[warp], m0, m1);
           if (h.flags & kDrawUnpaired) m0 = drop_open_tail(be, hd, nbe, ty * kTile + row, sx0, 16, h.rule == Z2D_FILL_EVEN_ODD, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
@@ -421,8 +485,34 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
       }
 
       // ---- composite the lane's 8 pixels
-      const DevDraw& d = A.draws[di];
       const RGBA16 spx = unpack_rgba(h.px_rgba);
+      if (tf.is32 && h.src_kind == Z2D_PARAM_PIXEL && h.op == Z2D_OP_SRC_OVER && !pre && !all_px &&
+          (h.reduces || h.precision == Z2D_PRECISION_INTEGER)) {
+        // fast path: single-pixel source, integer src_over.  Lanes 1..16 build the source at each coverage level
+        // (multisample.zig:223: alpha 16 * cov - 1; full coverage: unmasked), then every lane blends its pixels.
+        uint2* st = src_tab[warp];
+        if (lane >= 1 && lane <= 16) st[lane] = src_lanes(tf.f, spx, 16 * lane - 1, lane < 16);
+        __syncwarp();
+        if (row_ok && py >= h.ry0 && py < h.ry1 && (cov_e | cov_o) != 0u) {
+          const int lo = max(h.rx0 - px0, 0), hi = min(min(h.rx1, S.w) - px0, 8);
+          const uint32_t amask = tf.f.has_a ? 0xffffffffu : 0x00ffffffu;
+          const int full = aa == Z2D_AA_NONE ? 1 : 16;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
+            if (cov == 0 || i < lo || i >= hi) continue;
+            n_cov++;
+            uint32_t raw;
+            if (cov == full) raw = h.reduces ? h.paint_raw : src_over_x4(px[i * 32 + lane], st[16], amask);
+            else raw = src_over_x4(px[i * 32 + lane], st[cov], amask);
+            px[i * 32 + lane] = raw;
+          }
+        }
+        __syncwarp();
+        dirty = true;
+        continue;
+      }
+      const DevDraw& d = A.draws[di];
       for (int i = 0; i < 8; i++) {
         const int x = px0 + i;
         const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;

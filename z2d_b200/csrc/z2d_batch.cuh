@@ -74,6 +74,30 @@ struct DevDraw {
 
 constexpr uint32_t kDrawUnpaired = 1u;
 
+// What the host uploads per draw call (32 B); k_expand_draws turns it into the DevDraw the other kernels read.
+// Sources other than a single pixel and all stroke parameters live in side tables.
+constexpr uint32_t kNoIndex = 0xffffffffu;
+struct DrawIn {
+  uint32_t surface;
+  uint32_t opts;          // kind | aa << 1 | rule << 3 | op << 4 | precision << 9 | reduces << 10 | mode << 11
+  uint32_t paint_raw;
+  uint32_t px_rgba;       // inline single-pixel source (src_index == kNoIndex)
+  uint32_t src_index;     // index into the DevSrc side table
+  uint32_t stroke_index;  // index into the StrokeIn side table (strokes only)
+  double tolerance;
+};
+struct StrokeIn {
+  uint32_t cap, join;
+  uint32_t dash_begin, dash_count;
+  uint32_t pen_begin, pen_count;
+  uint32_t hair_aa, _pad;
+  double thickness, miter_limit, dash_offset, hair_tolerance;
+  double ctm[6], inv[6];
+};
+Z2D_HD uint32_t pack_draw_opts(uint32_t kind, uint32_t aa, uint32_t rule, uint32_t op, uint32_t precision, uint32_t reduces, uint32_t mode) {
+  return kind | (aa << 1) | (rule << 3) | (op << 4) | (precision << 9) | (reduces << 10) | (mode << 11);
+}
+
 struct DevEdge {
   double y0, y1, x_start, x_inc;
 };
@@ -84,7 +108,7 @@ struct DevEdge {
 struct DrawBox {  // tx0 < 0 => draw not valid
   int32_t tx0, tx1, ty0, ty1;
 };
-struct DrawHot {
+struct alignas(16) DrawHot {
   uint32_t aa, rule, op, precision;
   uint32_t reduces, paint_raw, px_rgba, src_kind;
   int32_t rx0, rx1, ry0, ry1;

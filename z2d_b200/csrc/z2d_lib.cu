@@ -101,7 +101,10 @@ struct z2d_ctx {
   // recorded batch
   PinnedVec<z2d_node> nodes;
   PinnedVec<DevSubPath> subpaths;
-  PinnedVec<DevDraw> draws;
+  PinnedVec<DrawIn> draws;
+  std::vector<StrokeIn> strokes;  // side tables of the batch
+  std::vector<DevSrc> srcs;
+  uint32_t iso_mode = 0, iso_node_begin = 0, iso_node_end = 0;  // the isolated draw of a 1-draw batch
   std::vector<z2d_sfc*> batch_sfcs;
   std::vector<DevGrad> grads;
   std::vector<float> stop_offsets;
@@ -114,6 +117,7 @@ struct z2d_ctx {
 
   // device state
   DevBuf d_pens, d_dashes;
+  DevBuf d_draws_in, d_strokes, d_srcs;
   DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -399,6 +403,8 @@ void clear_batch(z2d_ctx* c) {
   c->nodes.clear();
   c->subpaths.clear();
   c->draws.clear();
+  c->strokes.clear();
+  c->srcs.clear();
   for (z2d_sfc* s : c->batch_sfcs) s->batch_slot = -1;
   c->batch_sfcs.clear();
   c->grads.clear();
@@ -437,8 +443,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   };
   CK(c, c->d_counters.ensure(64));
   CK(c, cudaMemsetAsync(c->d_counters.p, 0, 64, st));
-  if (replay) launch_reset_draws(c->d_draws.as<DevDraw>(), n_draws, st);
   CK(c, cudaEventRecord(c->ev[0], st));
+  launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), n_draws, st);
 
   // K1: flatten (count, scan, emit)
   CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
@@ -521,7 +527,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   launch_raster(A, st);
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev[4], st));
-  launches += 8 + (replay ? 1 : 0);
+  launches += 9;
 
   z2d_stats& s = c->stats;
   memset(&s, 0, sizeof s);
@@ -542,14 +548,14 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 int run_isolated(z2d_ctx* c) {
   const BatchMeta& m = c->last;
   cudaStream_t st = c->stream;
-  const DevDraw& hd = c->draws.p[0];
   const GradTables T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
   uint32_t launches = 0, n_edges = 0;
   CK(c, cudaEventRecord(c->ev[0], st));
-  if (hd.mode == 1) {
-    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), hd.node_begin, hd.node_end,
+  launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), 1, st);
+  if (c->iso_mode == 1) {
+    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), c->iso_node_begin, c->iso_node_end,
                     c->d_dashes.as<double>(), T, st);
-    launches = 1;
+    launches = 2;
   } else {
     const uint32_t n_sp = m.n_sp;
     CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
@@ -565,7 +571,7 @@ int run_isolated(z2d_ctx* c) {
     launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
                         c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
     launch_direct_unbounded(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, c->batch_sfcs[0]->h, T, st);
-    launches = 6;
+    launches = 7;
   }
   CK(c, cudaGetLastError());
   for (int i = 1; i <= 4; i++) CK(c, cudaEventRecord(c->ev[i], st));
@@ -595,20 +601,24 @@ int flush_impl(z2d_ctx* c) {
 
   // 1. group draws by surface, keeping submission order inside each surface (draws on
   //    different surfaces are independent), and build the surface / work tables.
-  std::vector<uint32_t> per_sfc(n_sfc + 1, 0), remap(n_draws);
-  for (uint32_t i = 0; i < n_draws; i++) per_sfc[c->draws.p[i].surface + 1]++;
+  std::vector<uint32_t> per_sfc(n_sfc + 1, 0);
+  bool grouped = true;
+  for (uint32_t i = 0; i < n_draws; i++) {
+    per_sfc[c->draws.p[i].surface + 1]++;
+    grouped &= i == 0 || c->draws.p[i].surface >= c->draws.p[i - 1].surface;
+  }
   for (uint32_t s = 0; s < n_sfc; s++) per_sfc[s + 1] += per_sfc[s];
-  std::vector<DevDraw> sorted(n_draws);
-  {
-    std::vector<uint32_t> cur(per_sfc.begin(), per_sfc.end() - 1);
+  if (!grouped) {
+    std::vector<uint32_t> remap(n_draws), cur(per_sfc.begin(), per_sfc.end() - 1);
+    std::vector<DrawIn> sorted(n_draws);
     for (uint32_t i = 0; i < n_draws; i++) {
       uint32_t k = cur[c->draws.p[i].surface]++;
       remap[i] = k;
       sorted[k] = c->draws.p[i];
     }
+    for (size_t i = 0; i < c->subpaths.n; i++) c->subpaths.p[i].draw = remap[c->subpaths.p[i].draw];
+    memcpy(c->draws.p, sorted.data(), sizeof(DrawIn) * n_draws);
   }
-  for (size_t i = 0; i < c->subpaths.n; i++) c->subpaths.p[i].draw = remap[c->subpaths.p[i].draw];
-  memcpy(c->draws.p, sorted.data(), sizeof(DevDraw) * n_draws);
 
   std::vector<DevSurface> sfcs(n_sfc);
   std::vector<uint32_t> work_base(n_sfc + 1, 0);
@@ -636,7 +646,10 @@ int flush_impl(z2d_ctx* c) {
   // 2. upload the batch
   CK(c, upload(c, c->d_nodes, c->nodes.p, c->nodes.n * sizeof(z2d_node)));
   CK(c, upload(c, c->d_subpaths, c->subpaths.p, c->subpaths.n * sizeof(DevSubPath)));
-  CK(c, upload(c, c->d_draws, c->draws.p, c->draws.n * sizeof(DevDraw)));
+  CK(c, upload(c, c->d_draws_in, c->draws.p, c->draws.n * sizeof(DrawIn)));
+  CK(c, upload(c, c->d_strokes, c->strokes.data(), c->strokes.size() * sizeof(StrokeIn)));
+  CK(c, upload(c, c->d_srcs, c->srcs.data(), c->srcs.size() * sizeof(DevSrc)));
+  CK(c, c->d_draws.ensure(c->draws.n * sizeof(DevDraw)));
   CK(c, upload(c, c->d_sfcs, sfcs.data(), sfcs.size() * sizeof(DevSurface)));
   CK(c, upload(c, c->d_work_base, work_base.data(), work_base.size() * 4));
   CK(c, upload(c, c->d_grads, c->grads.data(), c->grads.size() * sizeof(DevGrad)));
@@ -652,10 +665,11 @@ int flush_impl(z2d_ctx* c) {
   m.n_tiles = n_tiles;
   m.n_work = n_work;
   m.n_nodes = c->nodes.n;
-  m.h2d_bytes = c->nodes.n * sizeof(z2d_node) + c->subpaths.n * sizeof(DevSubPath) + c->draws.n * sizeof(DevDraw) +
+  m.h2d_bytes = c->nodes.n * sizeof(z2d_node) + c->subpaths.n * sizeof(DevSubPath) + c->draws.n * sizeof(DrawIn) + c->strokes.size() * sizeof(StrokeIn) + c->srcs.size() * sizeof(DevSrc) +
+                c->pens.size() * 8 + c->dashes.size() * 8 +
                 sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + c->grads.size() * sizeof(DevGrad) +
                 c->stop_offsets.size() * 4 + c->stop_colors.size() * sizeof(float4);
-  int rc = (n_draws == 1 && c->draws.p[0].mode != 0) ? run_isolated(c) : run_pipeline(c, false);
+  int rc = (n_draws == 1 && ((c->draws.p[0].opts >> 11) & 3u) != 0) ? run_isolated(c) : run_pipeline(c, false);
   clear_batch(c);
   return rc;
 }
@@ -767,7 +781,8 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   DevBuf* bufs[] = {&c->d_blue, &c->d_nodes, &c->d_subpaths, &c->d_draws, &c->d_sfcs, &c->d_grads, &c->d_stop_off, &c->d_stop_col,
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
-                    &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col};
+                    &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
+                    &c->d_draws_in, &c->d_strokes, &c->d_srcs};
   for (DevBuf* b : bufs) b->release();
   c->nodes.release();
   c->subpaths.release();
@@ -934,19 +949,44 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   d.paint_raw = d.src.kind == Z2D_PARAM_PIXEL
                     ? pixel_to_raw(s->fmt, pattern->pixel.format, pattern->pixel.r, pattern->pixel.g, pattern->pixel.b, pattern->pixel.a)
                     : 0u;
-  d.ext[0] = f64_order(INFINITY);
-  d.ext[1] = f64_order(-INFINITY);
-  d.ext[2] = f64_order(INFINITY);
-  d.ext[3] = f64_order(-INFINITY);
-  const size_t save_nodes = c->nodes.n, save_sp = c->subpaths.n;
+  const size_t save_nodes = c->nodes.n, save_sp = c->subpaths.n, save_st = c->strokes.size(), save_src = c->srcs.size();
   const uint32_t di = (uint32_t)c->draws.n;
   rc = record_nodes(c, di, nodes, n);
-  d.node_begin = (uint32_t)save_nodes;
-  d.node_end = (uint32_t)c->nodes.n;
-  if (rc == Z2D_OK && !c->draws.push(d)) rc = Z2D_E_OUT_OF_MEMORY;
+  DrawIn in;
+  in.surface = d.surface;
+  in.opts = pack_draw_opts(d.kind, d.aa, d.rule, d.op, d.precision, d.reduces, d.mode);
+  in.paint_raw = d.paint_raw;
+  in.px_rgba = d.src.px_rgba;
+  in.tolerance = d.tolerance;
+  in.src_index = kNoIndex;
+  in.stroke_index = kNoIndex;
+  if (rc == Z2D_OK && d.src.kind != Z2D_PARAM_PIXEL) {
+    in.src_index = (uint32_t)c->srcs.size();
+    c->srcs.push_back(d.src);
+  }
+  if (rc == Z2D_OK && d.kind == 1) {
+    StrokeIn si;
+    memset(&si, 0, sizeof si);
+    si.cap = d.cap; si.join = d.join;
+    si.dash_begin = d.dash_begin; si.dash_count = d.dash_count;
+    si.pen_begin = d.pen_begin; si.pen_count = d.pen_count;
+    si.hair_aa = d.hair_aa; si.hair_tolerance = d.hair_tolerance;
+    si.thickness = d.thickness; si.miter_limit = d.miter_limit; si.dash_offset = d.dash_offset;
+    for (int k = 0; k < 6; k++) { si.ctm[k] = d.ctm[k]; si.inv[k] = d.inv[k]; }
+    in.stroke_index = (uint32_t)c->strokes.size();
+    c->strokes.push_back(si);
+  }
+  if (d.mode != 0) {
+    c->iso_mode = d.mode;
+    c->iso_node_begin = (uint32_t)save_nodes;
+    c->iso_node_end = (uint32_t)c->nodes.n;
+  }
+  if (rc == Z2D_OK && !c->draws.push(in)) rc = Z2D_E_OUT_OF_MEMORY;
   if (rc) {  // roll back: the failed call draws nothing
     c->nodes.n = save_nodes;
     c->subpaths.n = save_sp;
+    c->strokes.resize(save_st);
+    c->srcs.resize(save_src);
     c->grads.resize(save_g);
     c->stop_offsets.resize(save_o);
     c->stop_colors.resize(save_c);
