@@ -192,6 +192,10 @@ const char* z2d_last_error(const z2d_ctx* ctx); /* text of the last Z2D_E_DEVICE
  * private non-blocking stream.  (No reference equivalent: z2d has no device.) */
 int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out);
 void z2d_ctx_destroy(z2d_ctx* ctx);
+/* Recording is pipelined: every `max_draws` recorded draws the batch is handed to a worker thread that uploads
+ * and executes it while the caller keeps recording (results are unchanged: batches run in order on one stream).
+ * 0 disables the hand-over (one batch per flush point).  Default 32768.  Flushes first. */
+int32_t z2d_ctx_set_chunk(z2d_ctx* ctx, uint32_t max_draws);
 int32_t z2d_flush(z2d_ctx* ctx); /* enqueue everything recorded so far */
 int32_t z2d_sync(z2d_ctx* ctx);  /* flush + wait */
 

@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "blue_noise_table.h"
@@ -81,7 +84,7 @@ struct z2d_sfc {
   uint32_t fmt;
   int32_t w, h;
   size_t bytes;
-  int32_t batch_slot;  // index in the current batch's surface table, or -1
+  int32_t slot[2];  // index in the surface table of recording batch 0 / 1, or -1
 };
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
@@ -90,15 +93,8 @@ struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_r
   size_t n_nodes = 0, h2d_bytes = 0;
 };
 
-struct z2d_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = 148;
-  std::string last_error;
-  z2d_stats stats{};
-
-  // recorded batch
+struct Batch {  // one recorded command batch (host side)
+  int index = 0;
   PinnedVec<z2d_node> nodes;
   PinnedVec<DevSubPath> subpaths;
   PinnedVec<DrawIn> draws;
@@ -114,6 +110,26 @@ struct z2d_ctx {
   double pen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // parameters of the most recently built pen (thickness, tolerance, ctm)
   uint32_t pen_last_begin = 0, pen_last_count = 0;
   bool pen_cached = false;
+};
+
+struct z2d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string last_error;
+  z2d_stats stats{};
+
+  // recorded batches: the application thread records into `rec` while the worker may be executing the other one
+  Batch bat[2];
+  Batch* rec = &bat[0];
+  uint32_t chunk_draws = 32768;  // hand the recording batch to the worker every this many draws (0: never)
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  Batch* pending = nullptr;  // batch handed to the worker
+  bool busy = false, stop = false;
+  int async_rc = 0;          // first error of the batches the worker executed since the last wait
 
   // device state
   DevBuf d_pens, d_dashes;
@@ -336,9 +352,9 @@ double major_axis(const double* m, double radius) {
 // path uses) once per distinct (thickness, tolerance, CTM); the device only looks vertices up.
 void add_pen(z2d_ctx* c, DevDraw& d) {
   const double key[8] = {d.thickness, d.tolerance, d.ctm[0], d.ctm[1], d.ctm[2], d.ctm[3], d.ctm[4], d.ctm[5]};
-  if (c->pen_cached && memcmp(key, c->pen_key, sizeof key) == 0) {
-    d.pen_begin = c->pen_last_begin;
-    d.pen_count = c->pen_last_count;
+  if (c->rec->pen_cached && memcmp(key, c->rec->pen_key, sizeof key) == 0) {
+    d.pen_begin = c->rec->pen_last_begin;
+    d.pen_count = c->rec->pen_last_count;
     return;
   }
   const double radius = d.thickness / 2, tol = d.tolerance;
@@ -359,9 +375,9 @@ void add_pen(z2d_ctx* c, DevDraw& d) {
     }
   }
   const bool reflect = (d.ctm[0] * d.ctm[3] - d.ctm[1] * d.ctm[2]) < 0;
-  const size_t base = c->pens.size();
-  c->pens.resize(base + (size_t)n * 6);
-  double* v = c->pens.data() + base;
+  const size_t base = c->rec->pens.size();
+  c->rec->pens.resize(base + (size_t)n * 6);
+  double* v = c->rec->pens.data() + base;
   for (int i = 0; i < n; i++) {
     double t = 2 * M_PI * (double)i / (double)n;
     if (reflect) t = -t;
@@ -379,10 +395,10 @@ void add_pen(z2d_ctx* c, DevDraw& d) {
   }
   d.pen_begin = (uint32_t)(base / 6);
   d.pen_count = (uint32_t)n;
-  memcpy(c->pen_key, key, sizeof key);
-  c->pen_last_begin = d.pen_begin;
-  c->pen_last_count = d.pen_count;
-  c->pen_cached = true;
+  memcpy(c->rec->pen_key, key, sizeof key);
+  c->rec->pen_last_begin = d.pen_begin;
+  c->rec->pen_last_count = d.pen_count;
+  c->rec->pen_cached = true;
 }
 
 cudaError_t upload(z2d_ctx* c, DevBuf& b, const void* src, size_t bytes) {
@@ -399,20 +415,21 @@ int read_total(z2d_ctx* c, const uint32_t* dev, uint32_t& out) {
   return Z2D_OK;
 }
 
-void clear_batch(z2d_ctx* c) {
-  c->nodes.clear();
-  c->subpaths.clear();
-  c->draws.clear();
-  c->strokes.clear();
-  c->srcs.clear();
-  for (z2d_sfc* s : c->batch_sfcs) s->batch_slot = -1;
-  c->batch_sfcs.clear();
-  c->grads.clear();
-  c->stop_offsets.clear();
-  c->stop_colors.clear();
-  c->dashes.clear();
-  c->pens.clear();
-  c->pen_cached = false;
+void clear_batch(z2d_ctx* c, Batch& B) {
+  B.nodes.clear();
+  B.subpaths.clear();
+  B.draws.clear();
+  B.strokes.clear();
+  B.srcs.clear();
+  (void)c;
+  for (z2d_sfc* s : B.batch_sfcs) s->slot[B.index] = -1;
+  B.batch_sfcs.clear();
+  B.grads.clear();
+  B.stop_offsets.clear();
+  B.stop_colors.clear();
+  B.dashes.clear();
+  B.pens.clear();
+  B.pen_cached = false;
 }
 
 GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& sc) {
@@ -545,15 +562,15 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
 // Hairline strokes and the direct rasteriser with an unbounded operator are order / row-globally coupled
 // (slowpath.cuh); they run as a batch of exactly one draw.
-int run_isolated(z2d_ctx* c) {
+int run_isolated(z2d_ctx* c, Batch& B) {
   const BatchMeta& m = c->last;
   cudaStream_t st = c->stream;
   const GradTables T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
   uint32_t launches = 0, n_edges = 0;
   CK(c, cudaEventRecord(c->ev[0], st));
   launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), 1, st);
-  if (c->iso_mode == 1) {
-    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), c->iso_node_begin, c->iso_node_end,
+  if (B.iso_mode == 1) {
+    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), B.iso_node_begin, B.iso_node_end,
                     c->d_dashes.as<double>(), T, st);
     launches = 2;
   } else {
@@ -570,7 +587,7 @@ int run_isolated(z2d_ctx* c) {
     CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
     launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
                         c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
-    launch_direct_unbounded(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, c->batch_sfcs[0]->h, T, st);
+    launch_direct_unbounded(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, B.batch_sfcs[0]->h, T, st);
     launches = 7;
   }
   CK(c, cudaGetLastError());
@@ -590,41 +607,41 @@ int run_isolated(z2d_ctx* c) {
   return Z2D_OK;
 }
 
-int flush_impl(z2d_ctx* c) {
-  const uint32_t n_draws = (uint32_t)c->draws.n;
+int flush_impl(z2d_ctx* c, Batch& B) {
+  const uint32_t n_draws = (uint32_t)B.draws.n;
   if (n_draws == 0) {
-    clear_batch(c);
+    clear_batch(c, B);
     return Z2D_OK;
   }
   cudaStream_t st = c->stream;
-  const uint32_t n_sfc = (uint32_t)c->batch_sfcs.size();
+  const uint32_t n_sfc = (uint32_t)B.batch_sfcs.size();
 
   // 1. group draws by surface, keeping submission order inside each surface (draws on
   //    different surfaces are independent), and build the surface / work tables.
   std::vector<uint32_t> per_sfc(n_sfc + 1, 0);
   bool grouped = true;
   for (uint32_t i = 0; i < n_draws; i++) {
-    per_sfc[c->draws.p[i].surface + 1]++;
-    grouped &= i == 0 || c->draws.p[i].surface >= c->draws.p[i - 1].surface;
+    per_sfc[B.draws.p[i].surface + 1]++;
+    grouped &= i == 0 || B.draws.p[i].surface >= B.draws.p[i - 1].surface;
   }
   for (uint32_t s = 0; s < n_sfc; s++) per_sfc[s + 1] += per_sfc[s];
   if (!grouped) {
     std::vector<uint32_t> remap(n_draws), cur(per_sfc.begin(), per_sfc.end() - 1);
     std::vector<DrawIn> sorted(n_draws);
     for (uint32_t i = 0; i < n_draws; i++) {
-      uint32_t k = cur[c->draws.p[i].surface]++;
+      uint32_t k = cur[B.draws.p[i].surface]++;
       remap[i] = k;
-      sorted[k] = c->draws.p[i];
+      sorted[k] = B.draws.p[i];
     }
-    for (size_t i = 0; i < c->subpaths.n; i++) c->subpaths.p[i].draw = remap[c->subpaths.p[i].draw];
-    memcpy(c->draws.p, sorted.data(), sizeof(DrawIn) * n_draws);
+    for (size_t i = 0; i < B.subpaths.n; i++) B.subpaths.p[i].draw = remap[B.subpaths.p[i].draw];
+    memcpy(B.draws.p, sorted.data(), sizeof(DrawIn) * n_draws);
   }
 
   std::vector<DevSurface> sfcs(n_sfc);
   std::vector<uint32_t> work_base(n_sfc + 1, 0);
   uint32_t n_tiles = 0;
   for (uint32_t s = 0; s < n_sfc; s++) {
-    z2d_sfc* hs = c->batch_sfcs[s];
+    z2d_sfc* hs = B.batch_sfcs[s];
     DevSurface& d = sfcs[s];
     d.data = hs->data;
     d.fmt = hs->fmt;
@@ -641,22 +658,22 @@ int flush_impl(z2d_ctx* c) {
     work_base[s + 1] = work_base[s] + (uint32_t)d.tiles_y * chunks;
   }
   const uint32_t n_work = work_base[n_sfc];
-  const uint32_t n_sp = (uint32_t)c->subpaths.n;
+  const uint32_t n_sp = (uint32_t)B.subpaths.n;
 
   // 2. upload the batch
-  CK(c, upload(c, c->d_nodes, c->nodes.p, c->nodes.n * sizeof(z2d_node)));
-  CK(c, upload(c, c->d_subpaths, c->subpaths.p, c->subpaths.n * sizeof(DevSubPath)));
-  CK(c, upload(c, c->d_draws_in, c->draws.p, c->draws.n * sizeof(DrawIn)));
-  CK(c, upload(c, c->d_strokes, c->strokes.data(), c->strokes.size() * sizeof(StrokeIn)));
-  CK(c, upload(c, c->d_srcs, c->srcs.data(), c->srcs.size() * sizeof(DevSrc)));
-  CK(c, c->d_draws.ensure(c->draws.n * sizeof(DevDraw)));
+  CK(c, upload(c, c->d_nodes, B.nodes.p, B.nodes.n * sizeof(z2d_node)));
+  CK(c, upload(c, c->d_subpaths, B.subpaths.p, B.subpaths.n * sizeof(DevSubPath)));
+  CK(c, upload(c, c->d_draws_in, B.draws.p, B.draws.n * sizeof(DrawIn)));
+  CK(c, upload(c, c->d_strokes, B.strokes.data(), B.strokes.size() * sizeof(StrokeIn)));
+  CK(c, upload(c, c->d_srcs, B.srcs.data(), B.srcs.size() * sizeof(DevSrc)));
+  CK(c, c->d_draws.ensure(B.draws.n * sizeof(DevDraw)));
   CK(c, upload(c, c->d_sfcs, sfcs.data(), sfcs.size() * sizeof(DevSurface)));
   CK(c, upload(c, c->d_work_base, work_base.data(), work_base.size() * 4));
-  CK(c, upload(c, c->d_grads, c->grads.data(), c->grads.size() * sizeof(DevGrad)));
-  CK(c, upload(c, c->d_stop_off, c->stop_offsets.data(), c->stop_offsets.size() * 4));
-  CK(c, upload(c, c->d_stop_col, c->stop_colors.data(), c->stop_colors.size() * sizeof(float4)));
-  CK(c, upload(c, c->d_pens, c->pens.data(), c->pens.size() * 8));
-  CK(c, upload(c, c->d_dashes, c->dashes.data(), c->dashes.size() * 8));
+  CK(c, upload(c, c->d_grads, B.grads.data(), B.grads.size() * sizeof(DevGrad)));
+  CK(c, upload(c, c->d_stop_off, B.stop_offsets.data(), B.stop_offsets.size() * 4));
+  CK(c, upload(c, c->d_stop_col, B.stop_colors.data(), B.stop_colors.size() * sizeof(float4)));
+  CK(c, upload(c, c->d_pens, B.pens.data(), B.pens.size() * 8));
+  CK(c, upload(c, c->d_dashes, B.dashes.data(), B.dashes.size() * 8));
   BatchMeta& m = c->last;
   m.valid = true;
   m.n_draws = n_draws;
@@ -664,28 +681,80 @@ int flush_impl(z2d_ctx* c) {
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
   m.n_work = n_work;
-  m.n_nodes = c->nodes.n;
-  m.h2d_bytes = c->nodes.n * sizeof(z2d_node) + c->subpaths.n * sizeof(DevSubPath) + c->draws.n * sizeof(DrawIn) + c->strokes.size() * sizeof(StrokeIn) + c->srcs.size() * sizeof(DevSrc) +
-                c->pens.size() * 8 + c->dashes.size() * 8 +
-                sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + c->grads.size() * sizeof(DevGrad) +
-                c->stop_offsets.size() * 4 + c->stop_colors.size() * sizeof(float4);
-  int rc = (n_draws == 1 && ((c->draws.p[0].opts >> 11) & 3u) != 0) ? run_isolated(c) : run_pipeline(c, false);
-  clear_batch(c);
+  m.n_nodes = B.nodes.n;
+  m.h2d_bytes = B.nodes.n * sizeof(z2d_node) + B.subpaths.n * sizeof(DevSubPath) + B.draws.n * sizeof(DrawIn) + B.strokes.size() * sizeof(StrokeIn) + B.srcs.size() * sizeof(DevSrc) +
+                B.pens.size() * 8 + B.dashes.size() * 8 +
+                sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + B.grads.size() * sizeof(DevGrad) +
+                B.stop_offsets.size() * 4 + B.stop_colors.size() * sizeof(float4);
+  int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) != 0) ? run_isolated(c, B) : run_pipeline(c, false);
+  clear_batch(c, B);
   return rc;
 }
 
-int flush(z2d_ctx* c) {
-  int rc = flush_impl(c);
-  if (rc != Z2D_OK) clear_batch(c);
+int execute_batch(z2d_ctx* c, Batch& B) {
+  int rc = flush_impl(c, B);
+  if (rc != Z2D_OK) clear_batch(c, B);
   return rc;
+}
+
+// ---- worker: executes handed-over batches so that recording the next chunk overlaps upload + device work.
+// Only one of {worker, application thread} touches the device state at a time: every operation on the
+// application thread that uses the stream first waits for the worker to go idle.
+void worker_main(z2d_ctx* c) {
+  cudaSetDevice(c->device);
+  std::unique_lock<std::mutex> lk(c->mu);
+  for (;;) {
+    c->cv.wait(lk, [&] { return c->pending != nullptr || c->stop; });
+    if (c->pending == nullptr) return;  // stop requested and nothing queued
+    Batch* b = c->pending;
+    lk.unlock();
+    const int rc = execute_batch(c, *b);
+    lk.lock();
+    if (rc != Z2D_OK && c->async_rc == Z2D_OK) c->async_rc = rc;
+    c->pending = nullptr;
+    c->busy = false;
+    c->cv.notify_all();
+  }
+}
+
+int wait_idle(z2d_ctx* c) {  // returns (and clears) the first error of the batches executed by the worker
+  std::unique_lock<std::mutex> lk(c->mu);
+  c->cv.wait(lk, [&] { return !c->busy; });
+  const int rc = c->async_rc;
+  c->async_rc = Z2D_OK;
+  return rc;
+}
+
+// hand the recording batch to the worker and continue recording into the other one
+int kick(z2d_ctx* c) {
+  if (c->rec->draws.n == 0) return Z2D_OK;
+  int rc = wait_idle(c);
+  if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->pending = c->rec;
+    c->busy = true;
+  }
+  c->cv.notify_all();
+  c->rec = &c->bat[c->rec->index ^ 1];
+  return rc;
+}
+
+// everything recorded so far is enqueued on the stream when this returns
+int flush(z2d_ctx* c) {
+  cudaSetDevice(c->device);
+  int rc = wait_idle(c);
+  int rc2 = execute_batch(c, *c->rec);
+  return rc != Z2D_OK ? rc : rc2;
 }
 
 uint32_t batch_slot(z2d_ctx* c, z2d_sfc* s) {
-  if (s->batch_slot < 0) {
-    s->batch_slot = (int32_t)c->batch_sfcs.size();
-    c->batch_sfcs.push_back(s);
+  int32_t& slot = s->slot[c->rec->index];
+  if (slot < 0) {
+    slot = (int32_t)c->rec->batch_sfcs.size();
+    c->rec->batch_sfcs.push_back(s);
   }
-  return (uint32_t)s->batch_slot;
+  return (uint32_t)slot;
 }
 
 bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23-37
@@ -713,8 +782,8 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
     if (nodes[first].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
     first++;
   }
-  const uint32_t base = (uint32_t)c->nodes.n;
-  if (!c->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
+  const uint32_t base = (uint32_t)c->rec->nodes.n;
+  if (!c->rec->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
   const size_t m = n - first;
   size_t i = 0;
   while (i < m) {
@@ -728,7 +797,7 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
     sp.node_begin = base + (uint32_t)i;
     sp.node_end = base + (uint32_t)j;
     sp.last_of_draw = (j == m) ? 1u : 0u;
-    if (j - i > 1 && !c->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;  // a lone move_to draws nothing
+    if (j - i > 1 && !c->rec->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;  // a lone move_to draws nothing
     i = j;
   }
   return Z2D_OK;
@@ -753,6 +822,7 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   if (e != cudaSuccess) return Z2D_E_DEVICE;
   z2d_ctx* c = new z2d_ctx();
   c->device = device;
+  c->bat[1].index = 1;
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
@@ -776,17 +846,29 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
 void z2d_ctx_destroy(z2d_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  wait_idle(c);
+  if (c->worker.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->stop = true;
+    }
+    c->cv.notify_all();
+    c->worker.join();
+  }
   cudaStreamSynchronize(c->stream);
-  clear_batch(c);
+  clear_batch(c, c->bat[0]);
+  clear_batch(c, c->bat[1]);
   DevBuf* bufs[] = {&c->d_blue, &c->d_nodes, &c->d_subpaths, &c->d_draws, &c->d_sfcs, &c->d_grads, &c->d_stop_off, &c->d_stop_col,
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
                     &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
                     &c->d_draws_in, &c->d_strokes, &c->d_srcs};
   for (DevBuf* b : bufs) b->release();
-  c->nodes.release();
-  c->subpaths.release();
-  c->draws.release();
+  for (Batch& b : c->bat) {
+    b.nodes.release();
+    b.subpaths.release();
+    b.draws.release();
+  }
   if (c->h_total) cudaFreeHost(c->h_total);
   c->d_counters.release();
   c->d_boxes.release();
@@ -795,6 +877,14 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+int32_t z2d_ctx_set_chunk(z2d_ctx* c, uint32_t max_draws) {
+  if (!c) return Z2D_E_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  c->chunk_draws = max_draws;
+  return rc;
 }
 
 int32_t z2d_flush(z2d_ctx* c) {
@@ -815,6 +905,7 @@ int32_t z2d_sync(z2d_ctx* c) {
 int32_t z2d_get_stats(const z2d_ctx* cc, z2d_stats* out) {
   if (!cc || !out) return Z2D_E_INVALID_ARG;
   z2d_ctx* c = const_cast<z2d_ctx*>(cc);
+  wait_idle(c);
   if (c->stats_pending) {  // device counters and stage timings of the last batch
     cudaSetDevice(c->device);
     CK(c, cudaStreamSynchronize(c->stream));
@@ -854,7 +945,7 @@ int32_t z2d_surface_create(z2d_ctx* c, uint32_t format, int32_t width, int32_t h
   s->w = width;
   s->h = height;
   s->bytes = ((size_t)width * (size_t)height * (size_t)fmt_bits(format) + 7) / 8;
-  s->batch_slot = -1;
+  s->slot[0] = s->slot[1] = -1;
   const size_t alloc = (s->bytes + 31) & ~(size_t)15;  // word-granular atomics on packed formats may touch the padding
   cudaError_t e = cudaMalloc((void**)&s->data, alloc);
   if (e != cudaSuccess) {
@@ -881,7 +972,7 @@ void z2d_surface_destroy(z2d_sfc* s) {
   if (!s) return;
   z2d_ctx* c = s->ctx;
   cudaSetDevice(c->device);
-  if (s->batch_slot >= 0) flush(c);
+  flush(c);
   cudaStreamSynchronize(c->stream);
   cudaFree(s->data);
   delete s;
@@ -941,16 +1032,16 @@ int32_t z2d_surface_put_pixel(z2d_sfc* s, int32_t x, int32_t y, const z2d_pixel*
 
 // ------------------------------------------------------------------------- painter
 static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_node* nodes, size_t n, DevDraw& d) {
-  const size_t save_g = c->grads.size(), save_o = c->stop_offsets.size(), save_c = c->stop_colors.size();
-  int rc = pattern_to_src(*pattern, d.src, c->grads, c->stop_offsets, c->stop_colors);
+  const size_t save_g = c->rec->grads.size(), save_o = c->rec->stop_offsets.size(), save_c = c->rec->stop_colors.size();
+  int rc = pattern_to_src(*pattern, d.src, c->rec->grads, c->rec->stop_offsets, c->rec->stop_colors);
   if (rc) return rc;
   d.surface = batch_slot(c, s);
   d.reduces = (d.src.kind == Z2D_PARAM_PIXEL && (d.op == Z2D_OP_SRC || (d.op == Z2D_OP_SRC_OVER && px_is_opaque(pattern->pixel)))) ? 1u : 0u;
   d.paint_raw = d.src.kind == Z2D_PARAM_PIXEL
                     ? pixel_to_raw(s->fmt, pattern->pixel.format, pattern->pixel.r, pattern->pixel.g, pattern->pixel.b, pattern->pixel.a)
                     : 0u;
-  const size_t save_nodes = c->nodes.n, save_sp = c->subpaths.n, save_st = c->strokes.size(), save_src = c->srcs.size();
-  const uint32_t di = (uint32_t)c->draws.n;
+  const size_t save_nodes = c->rec->nodes.n, save_sp = c->rec->subpaths.n, save_st = c->rec->strokes.size(), save_src = c->rec->srcs.size();
+  const uint32_t di = (uint32_t)c->rec->draws.n;
   rc = record_nodes(c, di, nodes, n);
   DrawIn in;
   in.surface = d.surface;
@@ -961,8 +1052,8 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   in.src_index = kNoIndex;
   in.stroke_index = kNoIndex;
   if (rc == Z2D_OK && d.src.kind != Z2D_PARAM_PIXEL) {
-    in.src_index = (uint32_t)c->srcs.size();
-    c->srcs.push_back(d.src);
+    in.src_index = (uint32_t)c->rec->srcs.size();
+    c->rec->srcs.push_back(d.src);
   }
   if (rc == Z2D_OK && d.kind == 1) {
     StrokeIn si;
@@ -973,26 +1064,27 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     si.hair_aa = d.hair_aa; si.hair_tolerance = d.hair_tolerance;
     si.thickness = d.thickness; si.miter_limit = d.miter_limit; si.dash_offset = d.dash_offset;
     for (int k = 0; k < 6; k++) { si.ctm[k] = d.ctm[k]; si.inv[k] = d.inv[k]; }
-    in.stroke_index = (uint32_t)c->strokes.size();
-    c->strokes.push_back(si);
+    in.stroke_index = (uint32_t)c->rec->strokes.size();
+    c->rec->strokes.push_back(si);
   }
   if (d.mode != 0) {
-    c->iso_mode = d.mode;
-    c->iso_node_begin = (uint32_t)save_nodes;
-    c->iso_node_end = (uint32_t)c->nodes.n;
+    c->rec->iso_mode = d.mode;
+    c->rec->iso_node_begin = (uint32_t)save_nodes;
+    c->rec->iso_node_end = (uint32_t)c->rec->nodes.n;
   }
-  if (rc == Z2D_OK && !c->draws.push(in)) rc = Z2D_E_OUT_OF_MEMORY;
+  if (rc == Z2D_OK && !c->rec->draws.push(in)) rc = Z2D_E_OUT_OF_MEMORY;
   if (rc) {  // roll back: the failed call draws nothing
-    c->nodes.n = save_nodes;
-    c->subpaths.n = save_sp;
-    c->strokes.resize(save_st);
-    c->srcs.resize(save_src);
-    c->grads.resize(save_g);
-    c->stop_offsets.resize(save_o);
-    c->stop_colors.resize(save_c);
+    c->rec->nodes.n = save_nodes;
+    c->rec->subpaths.n = save_sp;
+    c->rec->strokes.resize(save_st);
+    c->rec->srcs.resize(save_src);
+    c->rec->grads.resize(save_g);
+    c->rec->stop_offsets.resize(save_o);
+    c->rec->stop_colors.resize(save_c);
     return rc;
   }
-  if (d.mode != 0 || c->nodes.n > kMaxBatchNodes || c->draws.n > kMaxBatchDraws) return flush(c);
+  if (d.mode != 0 || c->rec->nodes.n > kMaxBatchNodes || c->rec->draws.n > kMaxBatchDraws) return flush(c);
+  if (c->chunk_draws && c->rec->draws.n >= c->chunk_draws) return kick(c);  // asynchronous: recording continues
   return Z2D_OK;
 }
 
@@ -1002,7 +1094,6 @@ int32_t z2d_fill(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_n
   if (pattern->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(pattern->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;  // painter.zig:73-79
   if (n == 0) return Z2D_OK;                                         // painter.zig:81
   if (!is_closed_node_set(nodes, n)) return Z2D_E_PATH_NOT_CLOSED;   // painter.zig:82
-  cudaSetDevice(c->device);
   DevDraw d;
   memset(&d, 0, sizeof d);
   d.kind = 0;
@@ -1038,7 +1129,6 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   if (o->op >= Z2D_OP_COUNT || o->precision > 1 || o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X || o->line_cap_mode > Z2D_CAP_SQUARE ||
       o->line_join_mode > Z2D_JOIN_BEVEL || (o->n_dashes && !o->dashes))
     return Z2D_E_INVALID_ARG;
-  cudaSetDevice(c->device);
   // Dasher.validate (tess/Dasher.zig:15-29): all >= 0 and at least one > 0, else the stroke is not dashed
   bool dashed = false;
   for (size_t i = 0; i < o->n_dashes; i++) {
@@ -1066,14 +1156,14 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
     d.dash_offset = o->dash_offset;
     int frc = flush(c);  // isolated draw: everything recorded so far lands first
     if (frc) return frc;
-    const size_t save_d = c->dashes.size();
+    const size_t save_d = c->rec->dashes.size();
     if (dashed) {
-      d.dash_begin = (uint32_t)c->dashes.size();
+      d.dash_begin = (uint32_t)c->rec->dashes.size();
       d.dash_count = (uint32_t)o->n_dashes;
-      c->dashes.insert(c->dashes.end(), o->dashes, o->dashes + o->n_dashes);
+      c->rec->dashes.insert(c->rec->dashes.end(), o->dashes, o->dashes + o->n_dashes);
     }
     int32_t rc = record_draw(c, s, pattern, nodes, n, d);
-    if (rc != Z2D_OK) c->dashes.resize(std::min(save_d, c->dashes.size()));
+    if (rc != Z2D_OK) c->rec->dashes.resize(std::min(save_d, c->rec->dashes.size()));
     return rc;
   }
   // plotter state machine errors (stroke_plotter.zig:113,134; dashed_plotter.zig:128,178,203): a line_to / curve_to
@@ -1121,18 +1211,18 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   d.dash_offset = o->dash_offset;
   for (int i = 0; i < 6; i++) d.ctm[i] = o->ctm[i];
   invert_ctm(o->ctm, d.inv);
-  const size_t save_d = c->dashes.size(), save_p = c->pens.size();
+  const size_t save_d = c->rec->dashes.size(), save_p = c->rec->pens.size();
   if (dashed) {
-    d.dash_begin = (uint32_t)c->dashes.size();
+    d.dash_begin = (uint32_t)c->rec->dashes.size();
     d.dash_count = (uint32_t)o->n_dashes;
-    c->dashes.insert(c->dashes.end(), o->dashes, o->dashes + o->n_dashes);
+    c->rec->dashes.insert(c->rec->dashes.end(), o->dashes, o->dashes + o->n_dashes);
   }
   // the pen exists when a round join / cap is requested, or lazily once a curve is stroked (stroke_plotter.zig:56-59,139-144)
   if (d.join == Z2D_JOIN_ROUND || d.cap == Z2D_CAP_ROUND || has_curve) add_pen(c, d);
   int32_t rc = record_draw(c, s, pattern, nodes, n, d);
   if (rc != Z2D_OK && rc != Z2D_E_DEVICE) {
-    c->dashes.resize(std::min(save_d, c->dashes.size()));
-    c->pens.resize(std::min(save_p, c->pens.size()));
+    c->rec->dashes.resize(std::min(save_d, c->rec->dashes.size()));
+    c->rec->pens.resize(std::min(save_p, c->rec->pens.size()));
   }
   return rc;
 }

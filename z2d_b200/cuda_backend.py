@@ -35,6 +35,7 @@ def load_library():
         "z2d_ctx_create": (C.c_int32, [C.c_int32, vp, P(vp)]),
         "z2d_ctx_destroy": (None, [vp]),
         "z2d_flush": (C.c_int32, [vp]),
+        "z2d_ctx_set_chunk": (C.c_int32, [vp, C.c_uint32]),
         "z2d_sync": (C.c_int32, [vp]),
         "z2d_get_stats": (C.c_int32, [vp, P(abi.StatsPOD)]),
         "z2d_surface_create": (C.c_int32, [vp, C.c_uint32, C.c_int32, C.c_int32, P(abi.PixelPOD), P(vp)]),
@@ -62,7 +63,7 @@ def load_library():
     return lib
 
 
-EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_flush", "z2d_sync",
+EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
                     "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_paint_pixel",
@@ -149,6 +150,9 @@ class CudaBackend:
 
     def replay(self):
         self._check(self.lib.z2d_replay(self.ctx))
+
+    def set_chunk(self, max_draws):
+        self._check(self.lib.z2d_ctx_set_chunk(self.ctx, int(max_draws)))
 
     def flush(self):
         self._check(self.lib.z2d_flush(self.ctx))
