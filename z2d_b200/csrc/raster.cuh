@@ -151,38 +151,47 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
     if (TWO) p1[k] = ((wl1 >> k) & 1) ? ~0ull : 0ull;
   }
   const int sx_hi = sx0 + ncols;
-  const bool use_bits = n_be <= 64;
-  uint32_t i = 0;
-  while (true) {
-    if (use_bits) {  // iterate the crossing edges found by the classification pass
-      if (!cross_bits) break;
-      i = (uint32_t)__ffsll((long long)cross_bits) - 1u;
-      cross_bits &= cross_bits - 1;
-    } else {
-      if (i >= n_be) break;
-    }
-    const int4 h = __ldg(hd + i);
-    const bool a0 = hdr_active(h, ys0), a1 = TWO && hdr_active(h, ys0 + 1);
-    if ((a0 || a1) && (use_bits || (h.x <= sx_hi && h.y >= sx0))) {
-      const double4 ev = ld_edge(be + i);
-      const bool up = h.z < 0;
-      const double top = up ? ev.y : ev.x;
-      if (a0) {
-        const int c0 = edge_col(ev, top, ys0, sx0, ncols);
-        if (c0 >= 0) {
-          const uint64_t mask = ~0ull << c0;
-          if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, up);
-        }
-      }
-      if (TWO && a1) {
-        const int c1 = edge_col(ev, top, ys0 + 1, sx0, ncols);
-        if (c1 >= 0) {
-          const uint64_t mask = ~0ull << c1;
-          if (even_odd) p1[0] ^= mask; else wind_add<TWO ? W : 1>(p1, mask, up);
-        }
+  auto apply = [&](const double4& ev, bool up, bool a0, bool a1) {
+    const double top = up ? ev.y : ev.x;
+    if (a0) {
+      const int c0 = edge_col(ev, top, ys0, sx0, ncols);
+      if (c0 >= 0) {
+        const uint64_t mask = ~0ull << c0;
+        if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, up);
       }
     }
-    if (!use_bits) i++;
+    if (TWO && a1) {
+      const int c1 = edge_col(ev, top, ys0 + 1, sx0, ncols);
+      if (c1 >= 0) {
+        const uint64_t mask = ~0ull << c1;
+        if (even_odd) p1[0] ^= mask; else wind_add<TWO ? W : 1>(p1, mask, up);
+      }
+    }
+  };
+  if (n_be <= 64) {
+    // Which of the crossing edges are live on THIS lane's rows (warp-uniform loop, integer tests only) ...
+    uint64_t my0 = 0, my1 = 0, up_bits = 0;
+    for (uint64_t b = cross_bits; b; b &= b - 1) {
+      const int i = __ffsll((long long)b) - 1;
+      const int4 h = __ldg(hd + i);
+      const uint64_t bit = 1ull << i;
+      if (hdr_active(h, ys0)) my0 |= bit;
+      if (TWO && hdr_active(h, ys0 + 1)) my1 |= bit;
+      if (h.z < 0) up_bits |= bit;
+    }
+    // ... then every lane walks only its own edges: the warp iterates max-over-rows(edges per row) times, not once per
+    // crossing edge of the tile, and no lane idles on an edge that does not reach its rows.
+    for (uint64_t mine = my0 | my1; mine; mine &= mine - 1) {
+      const int i = __ffsll((long long)mine) - 1;
+      const uint64_t bit = 1ull << i;
+      apply(ld_edge(be + i), (up_bits & bit) != 0, (my0 & bit) != 0, (my1 & bit) != 0);
+    }
+  } else {
+    for (uint32_t i = 0; i < n_be; i++) {
+      const int4 h = __ldg(hd + i);
+      const bool a0 = hdr_active(h, ys0), a1 = TWO && hdr_active(h, ys0 + 1);
+      if ((a0 || a1) && h.x <= sx_hi && h.y >= sx0) apply(ld_edge(be + i), h.z < 0, a0, a1);
+    }
   }
   if (even_odd) {
     m0 = p0[0];
@@ -379,7 +388,7 @@ Z2D_D uint32_t src_over_x4(uint32_t raw, uint2 s, uint32_t amask) {
 }
 
 __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A) {
-  __shared__ uint32_t tile_px[kRasterThreads / 32][8 * 32];
+  __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
   __shared__ uint2 src_tab[kRasterThreads / 32][17];
   __shared__ int wdiff_s[kRasterThreads / 32][66];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -405,7 +414,8 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
   const uint32_t lb = A.list_off[w0], le = A.list_off[w0 + chunks];
   if (lb == le) return;
 
-  uint32_t* px = tile_px[warp];
+  uint32_t* px = tile_px[warp];  // pixel i of lane l lives at word (i >> 2) * 128 + l * 4 + (i & 3): 128-bit, conflict-free
+#define Z2D_PXI(i) ((((i) >> 2) << 7) + (lane << 2) + ((i) & 3))
   const int row = lane >> 1, half = lane & 1;
   const int py = ty * kTile + row;
   const int px0 = tx * kTile + half * 8;
@@ -417,6 +427,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
   tf.fmt = S.fmt;
   tf.is32 = S.fmt <= Z2D_FMT_RGBA;
   tf.f = fmt32_of(S.fmt);
+  const bool vec_ok = tf.is32 && row_ok && px0 + 8 <= S.w && ((row_idx + (size_t)px0) & 3) == 0;  // 2 x 128-bit global access
 
   for (uint32_t base = lb; base < le; base += 32) {
     uint2 it = make_uint2(0, 0);
@@ -477,9 +488,15 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
       if (!__any_sync(0xffffffffu, lane_work)) continue;
 
       if (!loaded) {  // lazy tile load: 8 pixels per lane
-        for (int i = 0; i < 8; i++) {
-          const int x = px0 + i;
-          px[i * 32 + lane] = (x < S.w && row_ok) ? load_raw(S.data, S.fmt, row_idx + (size_t)x) : 0u;
+        if (vec_ok) {
+          const uint4* g = reinterpret_cast<const uint4*>(S.data) + ((row_idx + (size_t)px0) >> 2);
+          reinterpret_cast<uint4*>(px)[lane] = g[0];
+          reinterpret_cast<uint4*>(px)[32 + lane] = g[1];
+        } else {
+          for (int i = 0; i < 8; i++) {
+            const int x = px0 + i;
+            px[Z2D_PXI(i)] = (x < S.w && row_ok) ? load_raw(S.data, S.fmt, row_idx + (size_t)x) : 0u;
+          }
         }
         loaded = true;
       }
@@ -496,17 +513,26 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
         if (row_ok && py >= h.ry0 && py < h.ry1 && (cov_e | cov_o) != 0u) {
           const int lo = max(h.rx0 - px0, 0), hi = min(min(h.rx1, S.w) - px0, 8);
           const uint32_t amask = tf.f.has_a ? 0xffffffffu : 0x00ffffffu;
-          const int full = aa == Z2D_AA_NONE ? 1 : 16;
+          const uint32_t full = aa == Z2D_AA_NONE ? 1u : 16u;
+          uint4 v[2] = {reinterpret_cast<uint4*>(px)[lane], reinterpret_cast<uint4*>(px)[32 + lane]};
+          uint32_t* w = reinterpret_cast<uint32_t*>(v);
+          const uint2 sfull = st[16];
+          if (lo == 0 && hi == 8 && cov_e == full * 0x01010101u && cov_o == cov_e) {  // interior: all 8 pixels fully covered
+            n_cov += 8;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
-            if (cov == 0 || i < lo || i >= hi) continue;
-            n_cov++;
-            uint32_t raw;
-            if (cov == full) raw = h.reduces ? h.paint_raw : src_over_x4(px[i * 32 + lane], st[16], amask);
-            else raw = src_over_x4(px[i * 32 + lane], st[cov], amask);
-            px[i * 32 + lane] = raw;
+            for (int i = 0; i < 8; i++) w[i] = h.reduces ? h.paint_raw : src_over_x4(w[i], sfull, amask);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const uint32_t cov = (((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xffu;
+              if (cov == 0 || i < lo || i >= hi) continue;
+              n_cov++;
+              if (cov == full) w[i] = h.reduces ? h.paint_raw : src_over_x4(w[i], sfull, amask);
+              else w[i] = src_over_x4(w[i], st[cov], amask);
+            }
           }
+          reinterpret_cast<uint4*>(px)[lane] = v[0];
+          reinterpret_cast<uint4*>(px)[32 + lane] = v[1];
         }
         __syncwarp();
         dirty = true;
@@ -521,7 +547,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
         const bool work = in_sfc && (pre || (in_reg && (all_px || cov != 0)));
         if (!__any_sync(0xffffffffu, work)) continue;
         if (!work) continue;
-        uint32_t raw = px[i * 32 + lane];
+        uint32_t raw = px[Z2D_PXI(i)];
         if (pre) {  // multisample.zig:96-110
           if (py < h.pre_y0 || (py > h.pre_y1 && py < h.pre_rows) || (py >= h.pre_y0 && py <= h.pre_y1 && x < h.pre_x)) raw = 0u;
         }
@@ -529,17 +555,24 @@ __global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A
           n_cov += cov > 0;
           raw = composite_cov(h, d, A.T, tf, spx, raw, cov, x, py);
         }
-        px[i * 32 + lane] = raw;
+        px[Z2D_PXI(i)] = raw;
       }
       dirty = true;
     }
   }
   if (dirty) {
-    for (int i = 0; i < 8; i++) {
-      const int x = px0 + i;
-      if (x < S.w && row_ok) store_raw(S.data, S.fmt, row_idx + (size_t)x, px[i * 32 + lane]);
+    if (vec_ok) {
+      uint4* g = reinterpret_cast<uint4*>(S.data) + ((row_idx + (size_t)px0) >> 2);
+      g[0] = reinterpret_cast<uint4*>(px)[lane];
+      g[1] = reinterpret_cast<uint4*>(px)[32 + lane];
+    } else {
+      for (int i = 0; i < 8; i++) {
+        const int x = px0 + i;
+        if (x < S.w && row_ok) store_raw(S.data, S.fmt, row_idx + (size_t)x, px[Z2D_PXI(i)]);
+      }
     }
   }
+#undef Z2D_PXI
   if (A.counters) {
     n_cov = __reduce_add_sync(0xffffffffu, n_cov);
     if (lane == 0 && n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
