@@ -243,6 +243,10 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
   const DevSubPath sp = sps[i];
+  if (sp.flags & kSpNodeParallel) {
+    sp_count[i] = 0;
+    return;
+  }
   DevDraw& d = draws[sp.draw];
   EdgeSink<false> sink;
   sink.scale = d.scale;
@@ -266,6 +270,7 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
   const DevSubPath sp = sps[i];
+  if (sp.flags & kSpNodeParallel) return;
   const DevDraw& d = draws[sp.draw];
   EdgeSink<true> sink;
   sink.scale = d.scale;
@@ -274,6 +279,91 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
   sink.draw = sp.draw;
   if (d.kind == 0) fill_subpath<true>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
   else stroke_subpath<true>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
+}
+
+// ---- node-parallel flattening of simple fill sub-paths (move_to, segments..., close_path; the host guarantees at least two
+// segments that move, so the implicit close applies, fill_plotter.zig:82-91).  The plotter's current point before a node is
+// the previous node's end point (a point equal to the current one is never added, fill_plotter.zig:46,107), so every node can
+// be flattened on its own: one thread per NODE instead of per sub-path -- 4-7x more threads for curve-heavy scenes and no
+// thread walks several curves back to back.
+__global__ void k_mark_nodes(const DevSubPath* __restrict__ sps, uint32_t n_sp, uint32_t* __restrict__ node_sp) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sp) return;
+  const DevSubPath sp = sps[i];
+  if (!(sp.flags & kSpNodeParallel)) return;
+  for (uint32_t k = sp.node_begin; k < sp.node_end; k++) node_sp[k] = i;
+}
+
+template <bool EMIT>
+__global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
+                                const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
+                                const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const uint32_t spi = node_sp[i];
+  if (spi == 0xffffffffu) {
+    if (!EMIT) counts[i] = 0;
+    return;
+  }
+  const DevSubPath sp = sps[spi];
+  const z2d_node nd = nodes[i];
+  if (nd.tag == Z2D_NODE_MOVE_TO) {
+    if (!EMIT) counts[i] = 0;
+    return;
+  }
+  DevDraw& d = draws[sp.draw];
+  EdgeSink<EMIT> sink;
+  sink.scale = d.scale;
+  if (EMIT) {
+    sink.out = edges + offs[i];
+    sink.out_draw = edge_draw + offs[i];
+    sink.draw = sp.draw;
+  }
+  const z2d_node pv = nodes[i - 1];  // move_to, line_to or curve_to
+  Pt last = pv.tag == Z2D_NODE_CURVE_TO ? Pt{pv.p[4], pv.p[5]} : Pt{pv.p[0], pv.p[1]};
+  auto line_to = [&](Pt p) {
+    if (!pt_eq(last, p)) {
+      sink.add(last, p);
+      last = p;
+    }
+  };
+  if (nd.tag == Z2D_NODE_LINE_TO) {
+    line_to({nd.p[0], nd.p[1]});
+  } else if (nd.tag == Z2D_NODE_CURVE_TO) {
+    const Pt a = last, b{nd.p[0], nd.p[1]}, c{nd.p[2], nd.p[3]}, e{nd.p[4], nd.p[5]};
+    if (pt_eq(a, b) && pt_eq(c, e)) {  // Spline.zig:39-42
+      line_to(e);
+    } else {
+      const double tol_sq = d.tolerance * d.tolerance;
+      Knots stack[kSplineStack];
+      int sp_n = 0;
+      stack[sp_n++] = Knots{a, b, c, e};
+      while (sp_n > 0) {  // Spline.zig:56-71, depth first, left half first
+        Knots k = stack[--sp_n];
+        if (knots_error_sq(k) < tol_sq || sp_n >= kSplineStack - 2) {
+          if (!pt_eq(k.a, a)) line_to(k.a);
+          continue;
+        }
+        Knots s2 = knots_split(k);
+        stack[sp_n++] = s2;
+        stack[sp_n++] = k;
+      }
+      line_to(e);
+    }
+  } else {  // close_path: the closing edge back to the sub-path's first point
+    const z2d_node mv = nodes[sp.node_begin];
+    line_to({mv.p[0], mv.p[1]});
+  }
+  if (!EMIT) {
+    counts[i] = sink.n;
+    if (sink.n > 0) {
+      atomicMin(&d.ext[0], f64_order(sink.top));
+      atomicMax(&d.ext[1], f64_order(sink.bottom));
+      atomicMin(&d.ext[2], f64_order(sink.left));
+      atomicMax(&d.ext[3], f64_order(sink.right));
+      atomicAdd(&d.n_edges, sink.n);
+    }
+  }
 }
 
 // =====================================================================================
@@ -691,6 +781,17 @@ void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* 
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st) {
   if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes);
+}
+void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
+                          DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw, cudaStream_t st) {
+  if (!n_nodes || !n_sp) return;
+  if (!emit) {
+    cudaMemsetAsync(node_sp, 0xff, (size_t)n_nodes * 4, st);
+    k_mark_nodes<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, node_sp);
+    k_flatten_nodes<false><<<blocks_for(n_nodes, 128), 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, counts, nullptr, nullptr, nullptr);
+  } else {
+    k_flatten_nodes<true><<<blocks_for(n_nodes, 128), 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw);
+  }
 }
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {
   if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, boxes, counters);

@@ -387,7 +387,10 @@ Z2D_D uint32_t src_over_x4(uint32_t raw, uint2 s, uint32_t amask) {
   return (lo | (hi << 8)) & amask;
 }
 
-__global__ void __launch_bounds__(kRasterThreads, 3) k_raster_tiles(RasterArgs A) {
+#ifndef Z2D_RASTER_MIN_CTAS
+#define Z2D_RASTER_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(RasterArgs A) {
   __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
   __shared__ uint2 src_tab[kRasterThreads / 32][17];
   __shared__ int wdiff_s[kRasterThreads / 32][66];

@@ -89,7 +89,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0;
   size_t n_nodes = 0, h2d_bytes = 0;
 };
 
@@ -101,6 +101,7 @@ struct Batch {  // one recorded command batch (host side)
   std::vector<StrokeIn> strokes;  // side tables of the batch
   std::vector<DevSrc> srcs;
   uint32_t iso_mode = 0, iso_node_begin = 0, iso_node_end = 0;  // the isolated draw of a 1-draw batch
+  uint32_t n_par_sp = 0;  // sub-paths flagged kSpNodeParallel
   std::vector<z2d_sfc*> batch_sfcs;
   std::vector<DevGrad> grads;
   std::vector<float> stop_offsets;
@@ -133,7 +134,7 @@ struct z2d_ctx {
 
   // device state
   DevBuf d_pens, d_dashes;
-  DevBuf d_draws_in, d_strokes, d_srcs;
+  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp;
   DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -419,6 +420,7 @@ void clear_batch(z2d_ctx* c, Batch& B) {
   B.nodes.clear();
   B.subpaths.clear();
   B.draws.clear();
+  B.n_par_sp = 0;
   B.strokes.clear();
   B.srcs.clear();
   (void)c;
@@ -463,20 +465,36 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, cudaEventRecord(c->ev[0], st));
   launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), n_draws, st);
 
-  // K1: flatten (count, scan, emit)
-  CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
+  // K1: flatten (count, scan, emit).  Count slots: one per sub-path (sequential plotters: strokes, irregular fills) followed,
+  // when the batch has node-parallel sub-paths, by one per node.
+  const uint32_t n_nodes = (uint32_t)m.n_nodes;
+  const bool par = m.n_par_sp != 0;
+  const uint32_t n_cnt = n_sp + (par ? n_nodes : 0u);
+  CK(c, c->d_sp_count.ensure((size_t)n_cnt * 4 + 16));
   launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
                        c->d_pens.p, c->d_dashes.as<double>(), st);
-  CK(c, scan(c->d_sp_count, c->d_sp_off, n_sp));
+  if (par) {
+    CK(c, c->d_node_sp.ensure((size_t)n_nodes * 4 + 16));
+    launch_flatten_nodes(false, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
+                         c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr, st);
+    launches += 3;
+  }
+  CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
   uint32_t n_edges = 0;
   {
-    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
+    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_cnt, n_edges);
     if (rc) return rc;
   }
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
   launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
                       c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
+  if (par) {
+    launch_flatten_nodes(true, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
+                         c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
+                         c->d_edge_draw.as<uint32_t>(), st);
+    launches += 1;
+  }
   CK(c, cudaEventRecord(c->ev[1], st));
 
   // K2: per-draw regions; (draw, tile-row) slots
@@ -678,6 +696,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.valid = true;
   m.n_draws = n_draws;
   m.n_sp = n_sp;
+  m.n_par_sp = B.n_par_sp;
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
   m.n_work = n_work;
@@ -773,7 +792,7 @@ bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23
 }
 
 // Split the node list at every move_to and append nodes + sub-path records to the batch.
-int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n) {
+int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n, bool allow_parallel) {
   // leading nodes before the first move_to: line_to / curve_to have no current point
   // (fill_plotter.zig:50,53 -> InternalError.InvalidState); a leading close_path is a no-op.
   size_t first = 0;
@@ -788,16 +807,35 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
   size_t i = 0;
   while (i < m) {
     size_t j = i + 1;
-    while (j < m && nodes[first + j].tag != Z2D_NODE_MOVE_TO) {
-      if (nodes[first + j].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+    // node-parallel flattening (kSpNodeParallel): move_to, segments..., one close_path at the very end, and at least two
+    // segments whose end differs from their start (then the plotter holds >= 3 points at the close, fill_plotter.zig:82)
+    const z2d_node* q = nodes + first;
+    double cx = q[i].p[0], cy = q[i].p[1];
+    int moving = 0;
+    bool simple = allow_parallel;
+    while (j < m && q[j].tag != Z2D_NODE_MOVE_TO) {
+      const uint32_t tag = q[j].tag;
+      if (tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+      if (tag == Z2D_NODE_CLOSE_PATH) {
+        if (j + 1 < m && q[j + 1].tag != Z2D_NODE_MOVE_TO) simple = false;  // something follows the close
+      } else {
+        const double ex = tag == Z2D_NODE_CURVE_TO ? q[j].p[4] : q[j].p[0], ey = tag == Z2D_NODE_CURVE_TO ? q[j].p[5] : q[j].p[1];
+        moving += (ex != cx || ey != cy);
+        cx = ex;
+        cy = ey;
+      }
       j++;
     }
+    simple = simple && q[j - 1].tag == Z2D_NODE_CLOSE_PATH && moving >= 2;
     DevSubPath sp;
     sp.draw = draw_index;
     sp.node_begin = base + (uint32_t)i;
     sp.node_end = base + (uint32_t)j;
-    sp.last_of_draw = (j == m) ? 1u : 0u;
-    if (j - i > 1 && !c->rec->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;  // a lone move_to draws nothing
+    sp.flags = ((j == m) ? kSpLastOfDraw : 0u) | (simple ? kSpNodeParallel : 0u);
+    if (j - i > 1) {  // a lone move_to draws nothing
+      if (!c->rec->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;
+      c->rec->n_par_sp += simple ? 1u : 0u;
+    }
     i = j;
   }
   return Z2D_OK;
@@ -862,7 +900,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
                     &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
-                    &c->d_draws_in, &c->d_strokes, &c->d_srcs};
+                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp};
   for (DevBuf* b : bufs) b->release();
   for (Batch& b : c->bat) {
     b.nodes.release();
@@ -1042,7 +1080,8 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
                     : 0u;
   const size_t save_nodes = c->rec->nodes.n, save_sp = c->rec->subpaths.n, save_st = c->rec->strokes.size(), save_src = c->rec->srcs.size();
   const uint32_t di = (uint32_t)c->rec->draws.n;
-  rc = record_nodes(c, di, nodes, n);
+  const uint32_t save_par = c->rec->n_par_sp;
+  rc = record_nodes(c, di, nodes, n, d.kind == 0 && d.mode == 0);
   DrawIn in;
   in.surface = d.surface;
   in.opts = pack_draw_opts(d.kind, d.aa, d.rule, d.op, d.precision, d.reduces, d.mode);
@@ -1076,6 +1115,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   if (rc) {  // roll back: the failed call draws nothing
     c->rec->nodes.n = save_nodes;
     c->rec->subpaths.n = save_sp;
+    c->rec->n_par_sp = save_par;
     c->rec->strokes.resize(save_st);
     c->rec->srcs.resize(save_src);
     c->rec->grads.resize(save_g);

@@ -26,7 +26,7 @@ def load_library():
         _build.build()
     if not os.path.exists(SO_PATH):
         raise RuntimeError(f"{SO_PATH} is missing: build it with `python -m z2d_b200.build` (no CPU fallback exists)")
-    lib = C.CDLL(SO_PATH)
+    lib = C.CDLL(os.environ.get("Z2D_CUDA_LIB", SO_PATH))  # Z2D_CUDA_LIB: tuning experiments with variant builds
     P = C.POINTER
     vp = C.c_void_p
     sigs = {
