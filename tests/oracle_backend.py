@@ -109,3 +109,23 @@ class OracleBackend:
 
     def sync(self):
         pass
+
+
+def render_scene(lib, scene, lo=0, hi=None, fmt=int(abi.Format.rgba)):
+    """Replay draws [lo, hi) of a workloads.Scene / FillScene through the CPU oracle; returns the raw surface bytes."""
+    hi = scene.n if hi is None else hi
+    buf = np.zeros(scene.width * scene.height * 4, dtype=np.uint8)
+    cmds = scene.draw_cmds(0, lo, hi)
+    P = C.POINTER
+    ptr = buf.ctypes.data_as(C.c_void_p)
+    for i in range(hi - lo):
+        pat = C.cast(C.c_void_p(int(cmds["pattern"][i])), P(abi.PatternPOD))
+        nodes = C.cast(C.c_void_p(int(cmds["nodes"][i])), P(abi.Node))
+        if int(cmds["kind"][i]) == 0:
+            rc = lib.z2d_ref_fill(ptr, fmt, scene.width, scene.height, pat, nodes, int(cmds["n_nodes"][i]),
+                                  C.cast(C.c_void_p(int(cmds["fill"][i])), P(abi.FillOptsPOD)))
+        else:
+            rc = lib.z2d_ref_stroke(ptr, fmt, scene.width, scene.height, pat, nodes, int(cmds["n_nodes"][i]),
+                                    C.cast(C.c_void_p(int(cmds["stroke"][i])), P(abi.StrokeOptsPOD)))
+        assert rc == 0, f"oracle draw {lo + i} failed with {rc}"
+    return buf
