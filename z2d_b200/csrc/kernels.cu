@@ -571,33 +571,34 @@ Z2D_D uint32_t find_surface_by(const DevSurface* sfcs, uint32_t n_sfc, const uin
 
 template <bool WRITE>
 __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
-                             uint32_t n_work, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
+                             const uint32_t* __restrict__ chunk_base, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
                              const uint32_t* __restrict__ off, uint2* __restrict__ items) {
-  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_work) return;
-  const uint32_t si = find_surface_by(sfcs, n_sfc, work_base, w);
+  // one block per (surface, chunk of kDrawChunk draws); threads stride over the surface's tile-rows, so every thread of a
+  // warp reads the SAME box at the same time (one broadcast transaction instead of 32 strided ones)
+  const uint32_t si = find_surface_by(sfcs, n_sfc, chunk_base, blockIdx.x);
   const DevSurface s = sfcs[si];
   const uint32_t n_draws = s.draw_end - s.draw_begin;
   const uint32_t chunks = (n_draws + kDrawChunk - 1) / kDrawChunk;
-  const uint32_t local = w - work_base[si];
-  const int band = (int)(local / chunks);
-  const uint32_t chunk = local % chunks;
+  const uint32_t chunk = blockIdx.x - chunk_base[si];
   const uint32_t b = s.draw_begin + chunk * kDrawChunk;
   const uint32_t e = min(b + kDrawChunk, s.draw_end);
-  uint32_t n = 0;
-  uint32_t o = WRITE ? off[w] : 0u;
-  for (uint32_t i = b; i < e; i++) {
-    const DrawBox d = boxes[i];
-    if (d.tx0 >= 0 && band >= d.ty0 && band <= d.ty1) {
-      if (WRITE) items[o + n] = make_uint2(i, (uint32_t)d.tx0 | ((uint32_t)d.tx1 << 16));
-      n++;
+  for (int band = (int)threadIdx.x; band < s.tiles_y; band += (int)blockDim.x) {
+    const uint32_t w = work_base[si] + (uint32_t)band * chunks + chunk;
+    uint32_t n = 0;
+    const uint32_t o = WRITE ? off[w] : 0u;
+    for (uint32_t i = b; i < e; i++) {
+      const int4 d = __ldg(reinterpret_cast<const int4*>(boxes) + i);  // {tx0, tx1, ty0, ty1}
+      if (d.x >= 0 && band >= d.z && band <= d.w) {
+        if (WRITE) items[o + n] = make_uint2(i, (uint32_t)d.x | ((uint32_t)d.y << 16));
+        n++;
+      }
     }
+    if (!WRITE) cnt[w] = n;
   }
-  if (!WRITE) cnt[w] = n;
 }
-template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DrawBox*, uint32_t*,
+template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, const uint32_t*, const DrawBox*, uint32_t*,
                                              const uint32_t*, uint2*);
-template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const uint32_t*, uint32_t, const DrawBox*, uint32_t*,
+template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const uint32_t*, const uint32_t*, const DrawBox*, uint32_t*,
                                             const uint32_t*, uint2*);
 
 }  // namespace z2d
@@ -809,13 +810,13 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
                         uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st) {
   if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges, band_hdr);
 }
-void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
-                       const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {
-  if (!n_work) return;
+void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
+                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {
+  if (!n_chunks) return;
   if (write)
-    k_band_lists<true><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, boxes, cnt, off, items);
+    k_band_lists<true><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
   else
-    k_band_lists<false><<<blocks_for(n_work, 128), 128, 0, st>>>(sfcs, n_sfc, work_base, n_work, boxes, cnt, off, items);
+    k_band_lists<false><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
 }
 void launch_raster(const RasterArgs& A, cudaStream_t st) {
   if (A.n_tiles) k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);

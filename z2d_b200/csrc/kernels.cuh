@@ -58,8 +58,9 @@ void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_of
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
                         uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st);
-void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, uint32_t n_work,
-                       const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
+// chunk_base[s] = number of (surface, kDrawChunk-draw chunk) blocks before surface s; one block per chunk
+void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
+                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
 void launch_raster(const RasterArgs& A, cudaStream_t st);
 // isolated single-draw modes (slowpath.cuh)
 void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const z2d_node* nodes, uint32_t node_begin,

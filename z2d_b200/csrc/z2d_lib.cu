@@ -89,7 +89,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0;
   size_t n_nodes = 0, h2d_bytes = 0;
 };
 
@@ -134,7 +134,7 @@ struct z2d_ctx {
 
   // device state
   DevBuf d_pens, d_dashes;
-  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp;
+  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp, d_chunk_base;
   DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -531,8 +531,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
   // K3b: ordered draw list per surface tile-row
   CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
-  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_boxes.as<DrawBox>(),
-                    c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
+  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), c->d_chunk_base.as<uint32_t>(), m.n_chunks,
+                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
   uint32_t n_items = 0;
   {
@@ -540,8 +540,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     if (rc) return rc;
   }
   CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
-  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), n_work, c->d_boxes.as<DrawBox>(), nullptr,
-                    c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
+  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), c->d_chunk_base.as<uint32_t>(), m.n_chunks,
+                    c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
   // K4: fused coverage + compositing
@@ -656,7 +656,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   }
 
   std::vector<DevSurface> sfcs(n_sfc);
-  std::vector<uint32_t> work_base(n_sfc + 1, 0);
+  std::vector<uint32_t> work_base(n_sfc + 1, 0), chunk_base(n_sfc + 1, 0);
   uint32_t n_tiles = 0;
   for (uint32_t s = 0; s < n_sfc; s++) {
     z2d_sfc* hs = B.batch_sfcs[s];
@@ -674,6 +674,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
     n_tiles += (uint32_t)d.tiles_x * (uint32_t)d.tiles_y;
     const uint32_t chunks = (d.draw_end - d.draw_begin + kDrawChunk - 1) / kDrawChunk;
     work_base[s + 1] = work_base[s] + (uint32_t)d.tiles_y * chunks;
+    chunk_base[s + 1] = chunk_base[s] + chunks;
   }
   const uint32_t n_work = work_base[n_sfc];
   const uint32_t n_sp = (uint32_t)B.subpaths.n;
@@ -687,6 +688,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   CK(c, c->d_draws.ensure(B.draws.n * sizeof(DevDraw)));
   CK(c, upload(c, c->d_sfcs, sfcs.data(), sfcs.size() * sizeof(DevSurface)));
   CK(c, upload(c, c->d_work_base, work_base.data(), work_base.size() * 4));
+  CK(c, upload(c, c->d_chunk_base, chunk_base.data(), chunk_base.size() * 4));
   CK(c, upload(c, c->d_grads, B.grads.data(), B.grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_stop_off, B.stop_offsets.data(), B.stop_offsets.size() * 4));
   CK(c, upload(c, c->d_stop_col, B.stop_colors.data(), B.stop_colors.size() * sizeof(float4)));
@@ -700,6 +702,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
   m.n_work = n_work;
+  m.n_chunks = chunk_base[n_sfc];
   m.n_nodes = B.nodes.n;
   m.h2d_bytes = B.nodes.n * sizeof(z2d_node) + B.subpaths.n * sizeof(DevSubPath) + B.draws.n * sizeof(DrawIn) + B.strokes.size() * sizeof(StrokeIn) + B.srcs.size() * sizeof(DevSrc) +
                 B.pens.size() * 8 + B.dashes.size() * 8 +
@@ -900,7 +903,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
                     &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
-                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp};
+                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp, &c->d_chunk_base};
   for (DevBuf* b : bufs) b->release();
   for (Batch& b : c->bat) {
     b.nodes.release();
