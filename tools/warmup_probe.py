@@ -21,7 +21,7 @@ cb.submit(cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), scene.n)
 cb.sync()
 zero = Pixel.rgba(0, 0, 0, 0)
 t0 = time.perf_counter()
-for it in range(80):
+for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 80):
     sfc.paint_pixel(zero)
     cb.replay()
     st = cb.stats()

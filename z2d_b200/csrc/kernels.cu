@@ -170,6 +170,27 @@ struct EdgeSink {
 
 constexpr int kSplineStack = 48;
 
+// Iterative Spline.decompose (tess/Spline.zig:37-71): depth first, left half first; emits the START point of every accepted
+// piece except the very first, then the end point.  Only right halves are stacked (the left half stays in registers), which
+// keeps the local-memory traffic of the flatten kernels to one 64-byte store per split and one load per emitted point.
+template <class F>
+Z2D_D void spline_decompose(Pt a, Pt b, Pt c, Pt d, double tol_sq, F&& line_to) {
+  if (pt_eq(a, b) && pt_eq(c, d)) {  // Spline.zig:39-42
+    line_to(d);
+    return;
+  }
+  Knots stack[kSplineStack];
+  int sp = 0;
+  Knots k{a, b, c, d};
+  for (;;) {
+    while (!(knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2)) stack[sp++] = knots_split(k);  // k becomes the left half
+    if (!pt_eq(k.a, a)) line_to(k.a);
+    if (sp == 0) break;
+    k = stack[--sp];
+  }
+  line_to(d);
+}
+
 // fill_plotter.plot (tess/fill_plotter.zig:21-97) restricted to one sub-path
 // (the plotter state resets at every move_to).
 template <bool EMIT>
@@ -200,25 +221,7 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
         break;
       case Z2D_NODE_CURVE_TO: {
         if (len == 0) break;
-        const Pt a = last, b{nd.p[0], nd.p[1]}, c{nd.p[2], nd.p[3]}, d{nd.p[4], nd.p[5]};
-        if (pt_eq(a, b) && pt_eq(c, d)) {  // Spline.zig:39-42
-          line_to(d);
-          break;
-        }
-        Knots stack[kSplineStack];
-        int sp = 0;
-        stack[sp++] = Knots{a, b, c, d};
-        while (sp > 0) {  // Spline.zig:56-71, depth first, left half first
-          Knots k = stack[--sp];
-          if (knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2) {
-            if (!pt_eq(k.a, a)) line_to(k.a);
-            continue;
-          }
-          Knots s2 = knots_split(k);
-          stack[sp++] = s2;
-          stack[sp++] = k;
-        }
-        line_to(d);
+        spline_decompose(last, {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, tol_sq, line_to);
         break;
       }
       default:  // close_path (fill_plotter.zig:72-92)
@@ -294,12 +297,20 @@ __global__ void k_mark_nodes(const DevSubPath* __restrict__ sps, uint32_t n_sp, 
   for (uint32_t k = sp.node_begin; k < sp.node_end; k++) node_sp[k] = i;
 }
 
-template <bool EMIT>
+// Thread per node for line_to / close_path (one edge at most); curve_to nodes are collected into a dense list (count pass)
+// and flattened by k_flatten_curves so that every lane of its warps runs the subdivision loop.
+template <bool EMIT, bool CURVES>
 __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
                                 const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
-                                const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw) {
+                                const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw,
+                                uint32_t* __restrict__ curve_list, uint32_t* __restrict__ n_curves) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_nodes) return;
+  if (CURVES) {  // i indexes the curve list
+    if (i >= *n_curves) return;
+    i = curve_list[i];
+  } else if (i >= n_nodes) {
+    return;
+  }
   const uint32_t spi = node_sp[i];
   if (spi == 0xffffffffu) {
     if (!EMIT) counts[i] = 0;
@@ -309,6 +320,10 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
   const z2d_node nd = nodes[i];
   if (nd.tag == Z2D_NODE_MOVE_TO) {
     if (!EMIT) counts[i] = 0;
+    return;
+  }
+  if (!CURVES && nd.tag == Z2D_NODE_CURVE_TO) {
+    if (!EMIT) curve_list[atomicAdd(n_curves, 1u)] = i;  // (nvcc aggregates the increment per warp)
     return;
   }
   DevDraw& d = draws[sp.draw];
@@ -330,6 +345,8 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
   if (nd.tag == Z2D_NODE_LINE_TO) {
     line_to({nd.p[0], nd.p[1]});
   } else if (nd.tag == Z2D_NODE_CURVE_TO) {
+    // Spline.decompose as ONE loop with one flatness test per trip, so the lanes of a warp stay converged on the
+    // expensive part (Knots.errorSq) whatever their subdivision depth
     const Pt a = last, b{nd.p[0], nd.p[1]}, c{nd.p[2], nd.p[3]}, e{nd.p[4], nd.p[5]};
     if (pt_eq(a, b) && pt_eq(c, e)) {  // Spline.zig:39-42
       line_to(e);
@@ -337,16 +354,15 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
       const double tol_sq = d.tolerance * d.tolerance;
       Knots stack[kSplineStack];
       int sp_n = 0;
-      stack[sp_n++] = Knots{a, b, c, e};
-      while (sp_n > 0) {  // Spline.zig:56-71, depth first, left half first
-        Knots k = stack[--sp_n];
-        if (knots_error_sq(k) < tol_sq || sp_n >= kSplineStack - 2) {
+      Knots k{a, b, c, e};
+      for (;;) {
+        if (!(knots_error_sq(k) < tol_sq || sp_n >= kSplineStack - 2)) {
+          stack[sp_n++] = knots_split(k);  // k becomes the left half
+        } else {
           if (!pt_eq(k.a, a)) line_to(k.a);
-          continue;
+          if (sp_n == 0) break;
+          k = stack[--sp_n];
         }
-        Knots s2 = knots_split(k);
-        stack[sp_n++] = s2;
-        stack[sp_n++] = k;
       }
       line_to(e);
     }
@@ -784,14 +800,21 @@ void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
   if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes);
 }
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
-                          DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw, cudaStream_t st) {
+                          DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,
+                          uint32_t* curve_list, cudaStream_t st) {
+  // node_sp: n_nodes entries; curve_list: n_nodes + 1 entries, the last one is the number of curves
   if (!n_nodes || !n_sp) return;
+  uint32_t* n_curves = curve_list + n_nodes;
+  const uint32_t nb = blocks_for(n_nodes, 128);
   if (!emit) {
     cudaMemsetAsync(node_sp, 0xff, (size_t)n_nodes * 4, st);
+    cudaMemsetAsync(n_curves, 0, 4, st);
     k_mark_nodes<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, node_sp);
-    k_flatten_nodes<false><<<blocks_for(n_nodes, 128), 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, counts, nullptr, nullptr, nullptr);
+    k_flatten_nodes<false, false><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, counts, nullptr, nullptr, nullptr, curve_list, n_curves);
+    k_flatten_nodes<false, true><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, counts, nullptr, nullptr, nullptr, curve_list, n_curves);
   } else {
-    k_flatten_nodes<true><<<blocks_for(n_nodes, 128), 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw);
+    k_flatten_nodes<true, false><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw, curve_list, n_curves);
+    k_flatten_nodes<true, true><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw, curve_list, n_curves);
   }
 }
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {

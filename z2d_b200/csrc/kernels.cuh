@@ -51,7 +51,8 @@ void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st);
 // node-parallel flattening of the sub-paths flagged kSpNodeParallel: count pass (emit = false: also builds node_sp) / emit pass
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
-                          DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw, cudaStream_t st);
+                          DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,
+                          uint32_t* curve_list /* n_nodes + 1 */, cudaStream_t st);
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st);
 void launch_expand_draws(const DrawIn* in, const StrokeIn* strokes, const DevSrc* srcs, DevDraw* draws, uint32_t n, cudaStream_t st);
 void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st);

@@ -233,24 +233,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
       case Z2D_NODE_CURVE_TO: {
         if (p_len == 0) break;
         const Pt a = p_last, b{nd.p[0], nd.p[1]}, cc{nd.p[2], nd.p[3]}, e{nd.p[4], nd.p[5]};
-        if (pt_eq(a, b) && pt_eq(cc, e)) {
-          line_to(e);
-          break;
-        }
-        Knots stack[kSplineStack];
-        int sp = 0;
-        stack[sp++] = Knots{a, b, cc, e};
-        while (sp > 0) {
-          Knots k = stack[--sp];
-          if (knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2) {
-            if (!pt_eq(k.a, a)) line_to(k.a);
-            continue;
-          }
-          Knots s2 = knots_split(k);
-          stack[sp++] = s2;
-          stack[sp++] = k;
-        }
-        line_to(e);
+        spline_decompose(a, b, cc, e, tol_sq, line_to);
         break;
       }
       default:  // close_path (polyline_plotter.zig:104-131)

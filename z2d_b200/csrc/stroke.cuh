@@ -450,25 +450,7 @@ struct Stroker {
   // iterative Spline.decompose (Spline.zig:37-71)
   template <class F>
   Z2D_D void spline(Pt a, Pt b, Pt cc, Pt d, F&& line_to) {
-    if (pt_eq(a, b) && pt_eq(cc, d)) {
-      line_to(d);
-      return;
-    }
-    const double tol_sq = c.tolerance * c.tolerance;
-    Knots stack[kSplineStack];
-    int sp = 0;
-    stack[sp++] = Knots{a, b, cc, d};
-    while (sp > 0) {
-      Knots k = stack[--sp];
-      if (knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2) {
-        if (!pt_eq(k.a, a)) line_to(k.a);
-        continue;
-      }
-      Knots s2 = knots_split(k);
-      stack[sp++] = s2;
-      stack[sp++] = k;
-    }
-    line_to(d);
+    spline_decompose(a, b, cc, d, c.tolerance * c.tolerance, line_to);
   }
 
   // =============================== undashed (stroke_plotter.zig:77-249)

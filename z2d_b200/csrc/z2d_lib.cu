@@ -134,7 +134,7 @@ struct z2d_ctx {
 
   // device state
   DevBuf d_pens, d_dashes;
-  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp, d_chunk_base;
+  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp, d_chunk_base, d_curve_list;
   DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -475,9 +475,11 @@ int run_pipeline(z2d_ctx* c, bool replay) {
                        c->d_pens.p, c->d_dashes.as<double>(), st);
   if (par) {
     CK(c, c->d_node_sp.ensure((size_t)n_nodes * 4 + 16));
+    CK(c, c->d_curve_list.ensure(((size_t)n_nodes + 1) * 4 + 16));
     launch_flatten_nodes(false, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
-                         c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr, st);
-    launches += 3;
+                         c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr,
+                         c->d_curve_list.as<uint32_t>(), st);
+    launches += 5;
   }
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
   uint32_t n_edges = 0;
@@ -492,8 +494,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   if (par) {
     launch_flatten_nodes(true, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
                          c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
-                         c->d_edge_draw.as<uint32_t>(), st);
-    launches += 1;
+                         c->d_edge_draw.as<uint32_t>(), c->d_curve_list.as<uint32_t>(), st);
+    launches += 2;
   }
   CK(c, cudaEventRecord(c->ev[1], st));
 
@@ -903,7 +905,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
                     &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
                     &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
                     &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
-                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp, &c->d_chunk_base};
+                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp, &c->d_chunk_base, &c->d_curve_list};
   for (DevBuf* b : bufs) b->release();
   for (Batch& b : c->bat) {
     b.nodes.release();
