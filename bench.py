@@ -285,7 +285,13 @@ def run_ours(args, rank, world, local_rank):
                                  "the tile-resident design touches each canvas tile once per batch, so DRAM traffic is far below this"},
             "stages_ms": {"flatten": st["ms_flatten"], "bin": st["ms_bin"], "lists": st["ms_lists"], "raster": r_ms,
                           "pipeline_total": float(np.mean(total_ms))},
-            "counters": {k: int(st[k]) for k in ("draws", "nodes", "edges", "band_edges", "tile_items", "tiles", "covered_px", "region_px")},
+            "counters": {k: int(st[k]) for k in ("draws", "nodes", "edges", "band_edges", "tile_items", "tiles", "covered_px", "region_px",
+                                                 "tile_pairs", "crossings")},
+            # per-tile coverage throughput of the raster kernel (north star): (draw, 16x16 tile) pairs and exact f64
+            # (edge, sub-scanline) crossings evaluated per second of k_raster_tiles time
+            "raster_throughput": {"tile_pairs_per_s": st["tile_pairs"] / (r_ms * 1e-3), "crossings_per_s": st["crossings"] / (r_ms * 1e-3),
+                                  "samples_per_s": st["tile_pairs"] * 4096 / (r_ms * 1e-3),
+                                  "composited_px_per_s": st["covered_px"] / (r_ms * 1e-3)},
             "roofline_composite": comp,
             "cpu_baseline": cpu,
         }
@@ -317,7 +323,7 @@ def composite_roofline(cb, args):
     peak, kind = peaks()
     achieved = 8.0 * n * n / (ms * 1e-3) / 1e9
     sfc.deinit()
-    return {"kernel": "k_composite_v4", "workload": "8192x8192 RGBA8 src_over, single-pixel source (BASELINE config 4 shape)",
+    return {"kernel": "k_composite_fast<integer, pixel source>", "workload": "8192x8192 RGBA8 src_over, single-pixel source (BASELINE config 4 shape)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "ms": ms,
             "mpix_per_s": n * n / (ms * 1e-3) / 1e6, "peak_kind": kind}
 

@@ -267,6 +267,8 @@ typedef struct z2d_stats {
   uint64_t region_px;     /* sum over draws of the evaluated bounding-region pixels */
   uint64_t kernel_launches;
   uint64_t h2d_bytes;     /* bytes uploaded for the batch */
+  uint64_t tile_pairs;    /* (draw, 16x16 tile) pairs the raster kernel evaluated coverage for */
+  uint64_t crossings;     /* (edge, sub-scanline) crossings evaluated exactly in f64 (Polygon.zig:305) */
   float ms_flatten, ms_bin, ms_lists, ms_raster, ms_total;
   float _pad;
 } z2d_stats;

@@ -264,7 +264,8 @@ class CompOpPOD(C.Structure):
 class StatsPOD(C.Structure):
     _fields_ = [("draws", C.c_uint64), ("nodes", C.c_uint64), ("edges", C.c_uint64), ("band_edges", C.c_uint64),
                 ("tile_items", C.c_uint64), ("tiles", C.c_uint64), ("covered_px", C.c_uint64), ("region_px", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("ms_flatten", C.c_float),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("tile_pairs", C.c_uint64), ("crossings", C.c_uint64),
+                ("ms_flatten", C.c_float),
                 ("ms_bin", C.c_float), ("ms_lists", C.c_float), ("ms_raster", C.c_float), ("ms_total", C.c_float),
                 ("_pad", C.c_float)]
 

@@ -684,6 +684,15 @@ __global__ void __launch_bounds__(256) k_composite_v4(const __grid_constant__ Co
 template <int PREC, int OP, bool SURF>
 Z2D_D uint32_t fast_px(const Fmt32& fd, const Fmt32& fs, const float* __restrict__ lut, uint32_t raw, RGBA16 s_const, RGBAF sf_const,
                        uint32_t sraw) {
+  if (PREC == Z2D_PRECISION_INTEGER && OP == Z2D_OP_SRC_OVER) {
+    // packed two-lane integer src_over (raster.cuh): half the ALU work of the per-channel form, identical results
+    const uint32_t amask = fd.has_a ? 0xffffffffu : 0x00ffffffu;
+    if (!SURF) return src_over_x4(raw, src_lanes(fd, s_const, 255, false), amask);
+    if (fs.rs == fd.rs) {  // same channel order: the source word splits straight into lanes (no alpha channel: sa = 255)
+      const uint32_t sw = fs.has_a ? sraw : (sraw | 0xff000000u);
+      return src_over_x4(raw, make_uint2(sw & 0x00ff00ffu, (sw >> 8) & 0x00ff00ffu), amask);
+    }
+  }
   RGBA16 d = unpack32(fd, raw);
   if (PREC == Z2D_PRECISION_INTEGER) {
     RGBA16 s = SURF ? unpack32(fs, sraw) : s_const;
@@ -708,33 +717,42 @@ Z2D_D void fast_loop(const CompArgs& A, const float* __restrict__ lut) {
   const uint4* __restrict__ src = SURF ? reinterpret_cast<const uint4*>(A.ops[0].src.sdata + ((size_t)A.src_start_y * (size_t)A.ops[0].src.sw) * 4) : nullptr;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + stride < n4; i += 2 * stride) {  // two independent 128-bit streams in flight per thread
-    uint4 a = dst[i], b = dst[i + stride];
-    uint4 sa = make_uint4(0, 0, 0, 0), sb = sa;
-    if (SURF) {
-      sa = __ldg(src + i);
-      sb = __ldg(src + i + stride);
+#ifndef Z2D_COMP_STREAMS
+#define Z2D_COMP_STREAMS 2
+#endif
+#ifdef Z2D_COMP_CS
+#define Z2D_LD(p) __ldcs(p)
+#define Z2D_ST(p, v) __stcs(p, v)
+#else
+#define Z2D_LD(p) (*(p))
+#define Z2D_ST(p, v) (*(p) = (v))
+#endif
+  for (; i + (Z2D_COMP_STREAMS - 1) * stride < n4; i += Z2D_COMP_STREAMS * stride) {  // independent 128-bit streams in flight per thread
+    uint4 v[Z2D_COMP_STREAMS], sv[Z2D_COMP_STREAMS];
+#pragma unroll
+    for (int k = 0; k < Z2D_COMP_STREAMS; k++) {
+      v[k] = Z2D_LD(dst + i + k * stride);
+      sv[k] = SURF ? __ldg(src + i + k * stride) : make_uint4(0, 0, 0, 0);
     }
-    a.x = fast_px<PREC, OP, SURF>(fd, fs, lut, a.x, sc, sfc, sa.x);
-    a.y = fast_px<PREC, OP, SURF>(fd, fs, lut, a.y, sc, sfc, sa.y);
-    a.z = fast_px<PREC, OP, SURF>(fd, fs, lut, a.z, sc, sfc, sa.z);
-    a.w = fast_px<PREC, OP, SURF>(fd, fs, lut, a.w, sc, sfc, sa.w);
-    b.x = fast_px<PREC, OP, SURF>(fd, fs, lut, b.x, sc, sfc, sb.x);
-    b.y = fast_px<PREC, OP, SURF>(fd, fs, lut, b.y, sc, sfc, sb.y);
-    b.z = fast_px<PREC, OP, SURF>(fd, fs, lut, b.z, sc, sfc, sb.z);
-    b.w = fast_px<PREC, OP, SURF>(fd, fs, lut, b.w, sc, sfc, sb.w);
-    dst[i] = a;
-    dst[i + stride] = b;
+#pragma unroll
+    for (int k = 0; k < Z2D_COMP_STREAMS; k++) {
+      v[k].x = fast_px<PREC, OP, SURF>(fd, fs, lut, v[k].x, sc, sfc, sv[k].x);
+      v[k].y = fast_px<PREC, OP, SURF>(fd, fs, lut, v[k].y, sc, sfc, sv[k].y);
+      v[k].z = fast_px<PREC, OP, SURF>(fd, fs, lut, v[k].z, sc, sfc, sv[k].z);
+      v[k].w = fast_px<PREC, OP, SURF>(fd, fs, lut, v[k].w, sc, sfc, sv[k].w);
+    }
+#pragma unroll
+    for (int k = 0; k < Z2D_COMP_STREAMS; k++) Z2D_ST(dst + i + k * stride, v[k]);
   }
-  if (i < n4) {
-    uint4 a = dst[i];
+  for (; i < n4; i += stride) {
+    uint4 a = Z2D_LD(dst + i);
     uint4 sa = make_uint4(0, 0, 0, 0);
     if (SURF) sa = __ldg(src + i);
     a.x = fast_px<PREC, OP, SURF>(fd, fs, lut, a.x, sc, sfc, sa.x);
     a.y = fast_px<PREC, OP, SURF>(fd, fs, lut, a.y, sc, sfc, sa.y);
     a.z = fast_px<PREC, OP, SURF>(fd, fs, lut, a.z, sc, sfc, sa.z);
     a.w = fast_px<PREC, OP, SURF>(fd, fs, lut, a.w, sc, sfc, sa.w);
-    dst[i] = a;
+    Z2D_ST(dst + i, a);
   }
 }
 
@@ -857,8 +875,11 @@ void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   const bool fast_px_src = one && o0.src.kind == Z2D_PARAM_PIXEL;
   const bool fast_sfc_src = one && o0.src.kind == Z2D_PARAM_SURFACE && o0.src.sfmt <= Z2D_FMT_RGBA && o0.src.sw == A.w && A.src_start_x == 0;
   if (fast_px_src || fast_sfc_src) {
-    unsigned fb = (unsigned)(((items + 1) / 2 + 255) / 256);  // two vectors per thread and iteration
-    const unsigned fcap = (unsigned)sm_count * 8u;             // persistent-style grid: 8 resident CTAs per SM
+    unsigned fb = (unsigned)(((items + 1) / 2 + 255) / 256);
+#ifndef Z2D_COMP_CTAS
+#define Z2D_COMP_CTAS 8
+#endif
+    const unsigned fcap = (unsigned)sm_count * Z2D_COMP_CTAS;  // persistent-style grid: resident CTAs per SM
     if (fb > fcap) fb = fcap;
     if (fb == 0) fb = 1;
     if (A.precision == Z2D_PRECISION_INTEGER) {

@@ -143,7 +143,7 @@ Z2D_D bool hdr_active(const int4& h, int ys) { return ys >= (h.z & 0x7fffffff) &
 
 template <int W, bool TWO>
 Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, uint64_t cross_bits, int ys0, int sx0,
-                      int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1) {
+                      int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
   uint64_t p0[W], p1[TWO ? W : 1];
 #pragma unroll
   for (int k = 0; k < W; k++) {  // start from the backdrop winding (two's complement, bit-sliced)
@@ -153,6 +153,7 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
   const int sx_hi = sx0 + ncols;
   auto apply = [&](const double4& ev, bool up, bool a0, bool a1) {
     const double top = up ? ev.y : ev.x;
+    n_eval += (uint32_t)a0 + (uint32_t)(TWO && a1);
     if (a0) {
       const int c0 = edge_col(ev, top, ys0, sx0, ncols);
       if (c0 >= 0) {
@@ -240,7 +241,7 @@ __device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, 
 // with warp-uniform be / hd / n_be; `wdiff` is the warp's 65-entry scratch in shared memory and ys_tile0 the tile's
 // first (sub-)scanline.
 Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, bool two, int sx0,
-                      int ncols, uint32_t rule, int* __restrict__ wdiff, uint64_t& m0, uint64_t& m1) {
+                      int ncols, uint32_t rule, int* __restrict__ wdiff, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
   const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
   const int lane = (int)(threadIdx.x & 31u);
   const int sx_hi = sx0 + ncols;
@@ -304,12 +305,12 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
   const bool full1 = !even_odd && (wl1 > (int)ncross || -wl1 > (int)ncross);
   const int b0 = full0 ? 0 : wl0, b1 = full1 ? 0 : wl1;
   if (ncross <= 7) {
-    if (two) cross_pass<5, true>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1);
-    else cross_pass<5, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1);
+    if (two) cross_pass<5, true>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
+    else cross_pass<5, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
   } else if (ncross <= 60) {
     uint64_t dummy = 0;
-    cross_pass<8, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, 0, m0, dummy);
-    if (two) cross_pass<8, false>(be, hd, n_be, cross_bits, ys0 + 1, sx0, ncols, even_odd, b1, 0, m1, dummy);
+    cross_pass<8, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, 0, m0, dummy, n_eval);
+    if (two) cross_pass<8, false>(be, hd, n_be, cross_bits, ys0 + 1, sx0, ncols, even_odd, b1, 0, m1, dummy, n_eval);
   } else {
     m0 = cross_row_wide(be, hd, n_be, ys0, sx0, ncols, even_odd, b0);
     m1 = two ? cross_row_wide(be, hd, n_be, ys0 + 1, sx0, ncols, even_odd, b1) : 0ull;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
   const int py = ty * kTile + row;
   const int px0 = tx * kTile + half * 8;
   bool loaded = false, dirty = false;
-  uint32_t n_cov = 0;
+  uint32_t n_cov = 0, n_eval = 0, n_pairs = 0;  // statistics: composited pixels, (edge, sub-scanline) crossings, (draw, tile) pairs
   const size_t row_idx = (size_t)py * (size_t)S.w;
   const bool row_ok = py < S.h;
   TileFmt tf;
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
       const bool pre = h.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
       const bool all_px = aa == Z2D_AA_SUPERSAMPLE_4X;  // every pixel of the region is composited, even at coverage 0
       if (!in_rows && !pre) continue;
+      n_pairs++;
       if (in_rows) {
         const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
         const uint32_t eb = A.band_off[bslot], ee = A.band_off[bslot + 1];
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         uint64_t m0 = 0, m1 = 0;
         const int sx0 = tx * kTile * Sc;
         if (Sc == 4) {
-          tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, wdiff_s[warp], m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, wdiff_s[warp], m0, m1, n_eval);
           if (h.flags & kDrawUnpaired) {
             m0 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m0);
             m1 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2 + 1, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m1);
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
-          tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, wdiff_s[warp], m0, m1);
+          tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, wdiff_s[warp], m0, m1, n_eval);
           if (h.flags & kDrawUnpaired) m0 = drop_open_tail(be, hd, nbe, ty * kTile + row, sx0, 16, h.rule == Z2D_FILL_EVEN_ODD, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
@@ -578,7 +580,12 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
 #undef Z2D_PXI
   if (A.counters) {
     n_cov = __reduce_add_sync(0xffffffffu, n_cov);
-    if (lane == 0 && n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
+    n_eval = __reduce_add_sync(0xffffffffu, n_eval);
+    if (lane == 0) {
+      if (n_cov) atomicAdd(&A.counters[0], (unsigned long long)n_cov);
+      if (n_pairs) atomicAdd(&A.counters[2], (unsigned long long)n_pairs);
+      if (n_eval) atomicAdd(&A.counters[3], (unsigned long long)n_eval);
+    }
   }
 }
 

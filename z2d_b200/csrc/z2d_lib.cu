@@ -952,10 +952,12 @@ int32_t z2d_get_stats(const z2d_ctx* cc, z2d_stats* out) {
   if (c->stats_pending) {  // device counters and stage timings of the last batch
     cudaSetDevice(c->device);
     CK(c, cudaStreamSynchronize(c->stream));
-    unsigned long long h[2] = {0, 0};
-    CK(c, cudaMemcpy(h, c->d_counters.p, 16, cudaMemcpyDeviceToHost));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CK(c, cudaMemcpy(h, c->d_counters.p, 32, cudaMemcpyDeviceToHost));
     c->stats.covered_px = h[0];
     c->stats.region_px = h[1];
+    c->stats.tile_pairs = h[2];
+    c->stats.crossings = h[3];
     cudaEventElapsedTime(&c->stats.ms_flatten, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->stats.ms_bin, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&c->stats.ms_lists, c->ev[2], c->ev[3]);
