@@ -158,6 +158,8 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     cb = CudaBackend(local_rank, stream=stream.cuda_stream)
+    if args.chunk >= 0:
+        cb.set_chunk(args.chunk)
     lib = cb.lib
 
     scene = workloads.cubic_paths_scene(args.paths, args.size, seed=sharding.scene_seed(sharding.BASE_SEED_C2, rank))
@@ -339,6 +341,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=-1, help="recorder chunk size for the e2e leg (-1: library default, 0: one batch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

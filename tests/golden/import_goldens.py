@@ -22,3 +22,15 @@ for p in sorted(src.glob("*.png")):
     manifest[p.name] = {"size": list(im.size), "mode": im.mode, "sha256": hashlib.sha256(p.read_bytes()).hexdigest()}
 (dst / "MANIFEST.json").write_text(json.dumps(manifest, indent=1, sort_keys=True) + "\n")
 print(len(manifest), "goldens imported")
+
+# The text scenes (spec/074, 080, 085) read glyph outlines from the reference's test fonts (spec/test-fonts; licences in the
+# reference's LICENSE file: Inter and Montserrat are OFL-1.1, DejaVu Sans is under the Bitstream Vera / DejaVu licence).
+fsrc = src.parent / "test-fonts"
+fdst = pathlib.Path(__file__).resolve().parent / "fonts"
+fdst.mkdir(exist_ok=True)
+fonts = {}
+for p in sorted(fsrc.glob("*.ttf")):
+    shutil.copyfile(p, fdst / p.name)
+    fonts[p.name] = {"bytes": p.stat().st_size, "sha256": hashlib.sha256(p.read_bytes()).hexdigest()}
+(fdst / "MANIFEST.json").write_text(json.dumps(fonts, indent=1, sort_keys=True) + "\n")
+print(len(fonts), "fonts imported")

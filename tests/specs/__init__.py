@@ -56,4 +56,4 @@ def bind(backend):
     return z
 
 
-from . import fills, strokes, compositing, extra  # noqa: E402,F401  (register scenes)
+from . import fills, strokes, compositing, extra, text  # noqa: E402,F401  (register scenes)

@@ -1,9 +1,4 @@
-# bench every variant library under z2d_b200/variants (tuning experiments)
-for so in z2d_b200/libz2d_cuda.so z2d_b200/variants/*.so; do
-  Z2D_CUDA_LIB=$PWD/$so python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null > /tmp/v.json
-  python - "$so" <<'PY'
-import json, sys
-b = json.load(open("/tmp/v.json"))
-print(sys.argv[1], "ms_per_step", round(b["ms_per_step"], 3), "raster", round(b["stages_ms"]["raster"], 3), "e2e", round(b["e2e"]["ms_per_step"], 2))
-PY
+# bench every variant library under z2d_b200/variants (tuning experiments); device-resident timing only, 20 replays each
+for so in z2d_b200/variants/*.so z2d_b200/variants/*.so; do
+  Z2D_CUDA_LIB=$PWD/$so python tools/warmup_probe.py 30 2>/dev/null | awk -v so="$so" '{r+=$6; t+=$8; n++} END {printf "%s raster %.3f total %.3f (mean of %d)\n", so, r/n, t/n, n}'
 done

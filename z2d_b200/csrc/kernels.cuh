@@ -4,7 +4,10 @@
 
 namespace z2d {
 
-constexpr int kRasterThreads = 256;  // 8 warps = 8 tiles per CTA
+#ifndef Z2D_RASTER_THREADS
+#define Z2D_RASTER_THREADS 256
+#endif
+constexpr int kRasterThreads = Z2D_RASTER_THREADS;  // one warp per tile
 constexpr uint32_t kDrawChunk = 256; // draws per band-list work item
 constexpr uint32_t kMaxCompOps = 8;
 
