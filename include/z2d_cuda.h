@@ -206,6 +206,14 @@ int32_t z2d_sync(z2d_ctx* ctx);  /* flush + wait */
  * (surface.zig:632,756-765).  initial_px may be NULL (zeroed). */
 int32_t z2d_surface_create(z2d_ctx* ctx, uint32_t format, int32_t width, int32_t height,
                            const z2d_pixel* initial_px, z2d_sfc** out);
+/* Band of a larger canvas (one very large canvas split into horizontal bands, one per GPU).  The surface stores
+ * rows [band_y0, band_y0 + band_rows) of a canvas `canvas_height` rows high; draw calls, put_pixel and pattern coordinates are
+ * given in CANVAS space and only the rows held here are touched, so replaying the same calls on every band and stacking the
+ * bands gives exactly the full-canvas result.  band_y0 must be a multiple of 16 (the tile height).  z2d_surface_height,
+ * byte_len, upload and download refer to the band's own rows.  z2d_composite on a band: offsets 0 and no surface params. */
+int32_t z2d_surface_create_band(z2d_ctx* ctx, uint32_t format, int32_t width, int32_t canvas_height, int32_t band_y0,
+                                int32_t band_rows, const z2d_pixel* initial_px, z2d_sfc** out);
+int32_t z2d_surface_band(const z2d_sfc* sfc, int32_t* band_y0, int32_t* canvas_height);
 void z2d_surface_destroy(z2d_sfc* sfc);
 size_t z2d_surface_byte_len(const z2d_sfc* sfc);
 int32_t z2d_surface_width(const z2d_sfc* sfc);

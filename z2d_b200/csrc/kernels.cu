@@ -440,7 +440,7 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
   if (d.n_edges == 0) return;
   const double top = f64_unorder(d.ext[0]), bottom = f64_unorder(d.ext[1]);
   const double left = f64_unorder(d.ext[2]), right = f64_unorder(d.ext[3]);
-  const int W = s.w, H = s.h;
+  const int W = s.w, H = s.vh;  // canvas height: a band surface clips afterwards
   const double sc = d.scale;
   // Polygon.inBox (tess/Polygon.zig:142-201)
   if (right < 0.0 || bottom < 0.0) return;
@@ -476,19 +476,30 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
     rx1 = clampi((int)ceil(right) + 1, rx0, W);
     if (rx1 <= rx0) return;
   }
+  // band surface: keep the part of the region that falls on the rows this surface holds
+  ry0 = max(ry0, s.y0);
+  ry1 = min(ry1, s.y0 + s.h);
+  const bool whole = unbounded && d.aa != Z2D_AA_NONE;  // the whole surface is touched (pre-clears / every pixel composited)
+  if (ry1 <= ry0 && !whole) return;
   d.rx0 = rx0; d.rx1 = rx1; d.ry0 = ry0; d.ry1 = ry1;
-  d.ey0 = ry0 >> kTileShift;
-  d.ey1 = (ry1 - 1) >> kTileShift;
-  if (unbounded && d.aa != Z2D_AA_NONE) {  // the whole surface is touched
+  if (ry1 > ry0) {
+    d.ey0 = ry0 >> kTileShift;  // canvas tile rows (edge binning)
+    d.ey1 = (ry1 - 1) >> kTileShift;
+  } else {
+    d.ey0 = 1;  // empty
+    d.ey1 = 0;
+  }
+  const int ty_org = s.y0 >> kTileShift;  // d.ty0 / d.ty1: tile rows of THIS surface (draw lists)
+  if (whole) {
     d.tx0 = 0; d.tx1 = s.tiles_x - 1; d.ty0 = 0; d.ty1 = s.tiles_y - 1;
   } else {
     d.tx0 = rx0 >> kTileShift; d.tx1 = (rx1 - 1) >> kTileShift;
-    d.ty0 = d.ey0; d.ty1 = d.ey1;
+    d.ty0 = d.ey0 - ty_org; d.ty1 = d.ey1 - ty_org;
   }
   d.valid = 1;
   boxes[i] = DrawBox{d.tx0, d.tx1, d.ty0, d.ty1};
   draw_bands[i] = (uint32_t)(d.ey1 - d.ey0 + 1);
-  if (counters) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
+  if (counters && ry1 > ry0) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
 }
 
 // second half of the setup: (draw, tile-row) slot base + the compact record the raster kernel reads
@@ -625,13 +636,15 @@ namespace z2d {
 // K5: surface-level compositor (SurfaceCompositor.run / StrideCompositor.run)
 // =====================================================================================
 Z2D_D uint32_t comp_pixel(const CompArgs& A, uint32_t raw, int dx, int dy, int sxp, int syp) {
-  // (dx,dy): destination pixel; (sxp,syp): matching source-space pixel (compositor.zig:389-436)
+  // (dx,dy): destination pixel; (sxp,syp): matching source-space pixel (compositor.zig:389-436).  Patterns are evaluated at
+  // the CANVAS row (a band surface holds canvas rows y_origin ...).
+  const int py = dy + A.y_origin;
   if (A.precision == Z2D_PRECISION_INTEGER) {
     RGBA16 d{0, 0, 0, 0}, s{0, 0, 0, 0};
     for (uint32_t k = 0; k < A.n_ops; k++) {
       const CompOp& o = A.ops[k];
-      s = o.has_src ? src_int(o.src, A.T, dx, dy, (size_t)o.src.sw * (size_t)syp + (size_t)sxp) : d;
-      d = o.has_dst ? src_int(o.dst, A.T, dx, dy, (size_t)o.dst.sw * (size_t)dy + (size_t)dx) : raw_to_rgba16(A.fmt, raw);
+      s = o.has_src ? src_int(o.src, A.T, dx, py, (size_t)o.src.sw * (size_t)syp + (size_t)sxp) : d;
+      d = o.has_dst ? src_int(o.dst, A.T, dx, py, (size_t)o.dst.sw * (size_t)dy + (size_t)dx) : raw_to_rgba16(A.fmt, raw);
       d = int_op(o.op, d, s);
     }
     return rgba16_to_raw(A.fmt, d);
@@ -639,8 +652,8 @@ Z2D_D uint32_t comp_pixel(const CompArgs& A, uint32_t raw, int dx, int dy, int s
   RGBAF d{0, 0, 0, 0}, s{0, 0, 0, 0};
   for (uint32_t k = 0; k < A.n_ops; k++) {
     const CompOp& o = A.ops[k];
-    s = o.has_src ? src_float(o.src, A.T, dx, dy, (size_t)o.src.sw * (size_t)syp + (size_t)sxp) : d;
-    d = o.has_dst ? src_float(o.dst, A.T, dx, dy, (size_t)o.dst.sw * (size_t)dy + (size_t)dx) : decode_raw(raw_to_rgba16(A.fmt, raw));
+    s = o.has_src ? src_float(o.src, A.T, dx, py, (size_t)o.src.sw * (size_t)syp + (size_t)sxp) : d;
+    d = o.has_dst ? src_float(o.dst, A.T, dx, py, (size_t)o.dst.sw * (size_t)dy + (size_t)dx) : decode_raw(raw_to_rgba16(A.fmt, raw));
     d = float_op(o.op, d, s);
   }
   return rgba16_to_raw(A.fmt, encode_raw(d));

@@ -38,6 +38,7 @@ struct CompArgs {  // SurfaceCompositor.run after clipping (compositor.zig:347-3
   int32_t w, h;
   int32_t dst_start_x, dst_start_y, src_start_x, src_start_y;
   int32_t scan_w, rows;
+  int32_t y_origin, _pad;  // band destination: canvas row of its first row (patterns are evaluated in canvas space)
   uint32_t n_ops, precision;
   GradTables T;
   CompOp ops[kMaxCompOps];

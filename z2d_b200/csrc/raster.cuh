@@ -410,11 +410,12 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
   }
   const DevSurface S = A.sfcs[si];
   const uint32_t lt = gt - S.tile_base;
-  const int ty = (int)(lt / (uint32_t)S.tiles_x), tx = (int)(lt % (uint32_t)S.tiles_x);
+  const int ty_local = (int)(lt / (uint32_t)S.tiles_x), tx = (int)(lt % (uint32_t)S.tiles_x);
+  const int ty = ty_local + (S.y0 >> kTileShift);  // canvas tile row (band surfaces start at row S.y0)
   // ordered draw list of this tile-row
   const uint32_t n_draws_s = S.draw_end - S.draw_begin;
   const uint32_t chunks = (n_draws_s + kDrawChunk - 1) / kDrawChunk;
-  const uint32_t w0 = A.work_base[si] + (uint32_t)ty * chunks;
+  const uint32_t w0 = A.work_base[si] + (uint32_t)ty_local * chunks;
   const uint32_t lb = A.list_off[w0], le = A.list_off[w0 + chunks];
   if (lb == le) return;
 
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
   const int px0 = tx * kTile + half * 8;
   bool loaded = false, dirty = false;
   uint32_t n_cov = 0, n_eval = 0, n_pairs = 0;  // statistics: composited pixels, (edge, sub-scanline) crossings, (draw, tile) pairs
-  const size_t row_idx = (size_t)py * (size_t)S.w;
-  const bool row_ok = py < S.h;
+  const size_t row_idx = (size_t)(py - S.y0) * (size_t)S.w;
+  const bool row_ok = py - S.y0 < S.h;
   TileFmt tf;
   tf.fmt = S.fmt;
   tf.is32 = S.fmt <= Z2D_FMT_RGBA;

@@ -14,8 +14,9 @@ namespace z2d {
 
 // compositeOpaque / compositeOpacity (raster/shared.zig:9-107) on one pixel of the surface
 Z2D_D void px_composite(const DevSurface& S, const DevDraw& d, const GradTables& T, int x, int y, bool use_opacity, int opacity) {
-  if (x < 0 || y < 0 || x >= S.w || y >= S.h) return;  // surface.zig:510,538,566
-  const size_t idx = (size_t)y * (size_t)S.w + (size_t)x;
+  if (x < 0 || y < 0 || x >= S.w || y >= S.vh) return;  // surface.zig:510,538,566
+  if (y < S.y0 || y >= S.y0 + S.h) return;              // band surface: row not held here
+  const size_t idx = (size_t)(y - S.y0) * (size_t)S.w + (size_t)x;
   const uint32_t fmt = S.fmt;
   uint32_t raw = load_raw(S.data, fmt, idx);
   if (d.op == Z2D_OP_CLEAR) {
@@ -49,7 +50,7 @@ Z2D_D uint32_t hl_err_inc(int a, int b) {  // hairline.zig:383-396
 }
 
 Z2D_D void hl_draw_line(const HairCtx& c, int x0, int y0, int x1, int y1) {  // hairline.zig:94-364
-  const int W = c.S.w, H = c.S.h;
+  const int W = c.S.w, H = c.S.vh;
   if ((x0 < 0 || x0 >= W) && (x1 < 0 || x1 >= W)) return;
   if ((y0 < 0 || y0 >= H) && (y1 < 0 || y1 >= H)) return;
   const int adx = abs(x1 - x0), ady = abs(y1 - y0);
@@ -257,8 +258,9 @@ __global__ void k_direct_unbounded(const DevSurface* __restrict__ sfcs, const De
                                    const DevEdge* __restrict__ edges, uint32_t n_edges, GradTables T) {
   const DevDraw& d = draws[draw_index];
   const DevSurface S = sfcs[d.surface];
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
-  if (y >= S.h) return;
+  const int yl = blockIdx.x * blockDim.x + threadIdx.x;  // row of this surface; y: row of the canvas
+  if (yl >= S.h) return;
+  const int y = yl + S.y0;
   const int W = S.w;
   {  // direct.zig:57-67: no y-breakpoint at or below scanline 0 => the whole draw is a no-op
     bool any = false;
@@ -322,12 +324,12 @@ __global__ void k_direct_unbounded(const DevSurface* __restrict__ sfcs, const De
     n_filtered++;
   }
   if (n_filtered == 0) {  // direct.zig:88-92
-    for (int x = 0; x < W; x++) store_raw(S.data, S.fmt, (size_t)y * W + x, 0u);
+    for (int x = 0; x < W; x++) store_raw(S.data, S.fmt, (size_t)yl * W + x, 0u);
     return;
   }
   if (n_pairs == 0) return;  // nothing processed: the row is left untouched
   for (int x = 0; x < W; x++) {
-    const size_t idx = (size_t)y * (size_t)W + (size_t)x;
+    const size_t idx = (size_t)yl * (size_t)W + (size_t)x;
     if (x >= last_sx && x < last_ex) {
       if (n_pairs > 1) store_raw(S.data, S.fmt, idx, 0u);  // cleared by the previous pair's tail clear
       px_composite(S, d, T, x, y, false, 255);

@@ -29,6 +29,9 @@ struct DevSurface {
   uint32_t tile_base;   // first global tile index of this surface in the batch
   uint32_t band_base;   // first global tile-row ("band") index
   uint32_t draw_begin, draw_end;  // draws of this surface (draws are grouped by surface, order preserved)
+  // band surfaces (z2d_surface_create_band): the memory holds rows [y0, y0 + h) of a virtual canvas vh rows high; all
+  // geometry, regions and pattern coordinates stay in canvas space.  Ordinary surfaces: y0 = 0, vh = h.
+  int32_t y0, vh;
 };
 
 struct DevSubPath {  // one move_to ... run of nodes (state resets at every move_to)

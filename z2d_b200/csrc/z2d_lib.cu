@@ -85,6 +85,7 @@ struct z2d_sfc {
   int32_t w, h;
   size_t bytes;
   int32_t slot[2];  // index in the surface table of recording batch 0 / 1, or -1
+  int32_t y0 = 0, vh = 0;  // band surface: rows [y0, y0 + h) of a canvas vh rows high (ordinary surface: 0, h)
 };
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
@@ -669,6 +670,8 @@ int flush_impl(z2d_ctx* c, Batch& B) {
     d.h = hs->h;
     d.tiles_x = (hs->w + kTile - 1) / kTile;
     d.tiles_y = (hs->h + kTile - 1) / kTile;
+    d.y0 = hs->y0;
+    d.vh = hs->vh;
     d.tile_base = n_tiles;
     d.band_base = 0;
     d.draw_begin = per_sfc[s];
@@ -989,6 +992,7 @@ int32_t z2d_surface_create(z2d_ctx* c, uint32_t format, int32_t width, int32_t h
   s->fmt = format;
   s->w = width;
   s->h = height;
+  s->vh = height;
   s->bytes = ((size_t)width * (size_t)height * (size_t)fmt_bits(format) + 7) / 8;
   s->slot[0] = s->slot[1] = -1;
   const size_t alloc = (s->bytes + 31) & ~(size_t)15;  // word-granular atomics on packed formats may touch the padding
@@ -1010,6 +1014,26 @@ int32_t z2d_surface_create(z2d_ctx* c, uint32_t format, int32_t width, int32_t h
     return fail(c, "surface init", e);
   }
   *out = s;
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_create_band(z2d_ctx* c, uint32_t format, int32_t width, int32_t canvas_height, int32_t band_y0, int32_t band_rows,
+                                const z2d_pixel* initial_px, z2d_sfc** out) {
+  if (!out) return Z2D_E_INVALID_ARG;
+  *out = nullptr;
+  if (canvas_height < 1) return Z2D_E_INVALID_HEIGHT;
+  if (band_y0 < 0 || band_rows < 1 || (band_y0 & (kTile - 1)) != 0 || band_y0 + band_rows > canvas_height) return Z2D_E_INVALID_ARG;
+  int rc = z2d_surface_create(c, format, width, band_rows, initial_px, out);
+  if (rc) return rc;
+  (*out)->y0 = band_y0;
+  (*out)->vh = canvas_height;
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_band(const z2d_sfc* s, int32_t* band_y0, int32_t* canvas_height) {
+  if (!s) return Z2D_E_INVALID_ARG;
+  if (band_y0) *band_y0 = s->y0;
+  if (canvas_height) *canvas_height = s->vh;
   return Z2D_OK;
 }
 
@@ -1064,7 +1088,9 @@ int32_t z2d_surface_paint_pixel(z2d_sfc* s, const z2d_pixel* px) {
 
 int32_t z2d_surface_put_pixel(z2d_sfc* s, int32_t x, int32_t y, const z2d_pixel* px) {
   if (!s || !px || px->format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
-  if (x < 0 || y < 0 || x >= s->w || y >= s->h) return Z2D_OK;  // surface.zig:520,770
+  if (x < 0 || y < 0 || x >= s->w || y >= s->vh) return Z2D_OK;  // surface.zig:520,770
+  y -= s->y0;  // band surface: canvas row -> row held here
+  if (y < 0 || y >= s->h) return Z2D_OK;
   z2d_ctx* c = s->ctx;
   cudaSetDevice(c->device);
   int rc = flush(c);
@@ -1294,6 +1320,11 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   cudaSetDevice(c->device);
   int rc = flush(c);  // ordering: everything recorded so far lands first
   if (rc) return rc;
+  if (dst->y0 != 0 || dst->vh != dst->h) {  // band destination: whole-band operations with generated sources only
+    if (dst_x != 0 || dst_y != 0) return Z2D_E_INVALID_ARG;
+    for (size_t k = 0; k < n_ops; k++)
+      if (ops[k].src.kind == Z2D_PARAM_SURFACE || ops[k].dst.kind == Z2D_PARAM_SURFACE) return Z2D_E_INVALID_ARG;
+  }
   // compositor.zig:311-374
   if (n_ops == 0) return Z2D_OK;
   if (dst_x >= dst->w || dst_y >= dst->h) return Z2D_OK;
@@ -1327,6 +1358,7 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   A.fmt = dst->fmt;
   A.w = dst->w;
   A.h = dst->h;
+  A.y_origin = dst->y0;
   A.src_start_x = src_start_x;
   A.src_start_y = src_start_y;
   A.dst_start_x = src_start_x + dst_x;

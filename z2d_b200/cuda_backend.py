@@ -39,6 +39,8 @@ def load_library():
         "z2d_sync": (C.c_int32, [vp]),
         "z2d_get_stats": (C.c_int32, [vp, P(abi.StatsPOD)]),
         "z2d_surface_create": (C.c_int32, [vp, C.c_uint32, C.c_int32, C.c_int32, P(abi.PixelPOD), P(vp)]),
+        "z2d_surface_create_band": (C.c_int32, [vp, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(abi.PixelPOD), P(vp)]),
+        "z2d_surface_band": (C.c_int32, [vp, P(C.c_int32), P(C.c_int32)]),
         "z2d_surface_destroy": (None, [vp]),
         "z2d_surface_byte_len": (C.c_size_t, [vp]),
         "z2d_surface_width": (C.c_int32, [vp]),
@@ -64,7 +66,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
-                    "z2d_get_stats", "z2d_surface_create", "z2d_surface_destroy", "z2d_surface_byte_len",
+                    "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
                     "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_paint_pixel",
                     "z2d_surface_put_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
@@ -99,6 +101,12 @@ class CudaBackend:
         out = C.c_void_p()
         px = C.byref(initial_px.pod()) if initial_px is not None else None
         self._check(self.lib.z2d_surface_create(self.ctx, int(fmt), w, h, px, C.byref(out)))
+        return out
+
+    def surface_create_band(self, fmt, w, canvas_h, y0, rows, initial_px):
+        out = C.c_void_p()
+        px = C.byref(initial_px.pod()) if initial_px is not None else None
+        self._check(self.lib.z2d_surface_create_band(self.ctx, int(fmt), w, canvas_h, y0, rows, px, C.byref(out)))
         return out
 
     def surface_destroy(self, hd):

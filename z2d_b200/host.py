@@ -551,15 +551,22 @@ def default_backend():
 
 
 class Surface:
-    def __init__(self, format, width, height, initial_px=None, backend=None):  # Surface.init / initPixel (surface.zig:97-157)
+    def __init__(self, format, width, height, initial_px=None, backend=None, band=None):
+        """Surface.init / initPixel (surface.zig:97-157).  band=(y0, rows): hold only rows [y0, y0 + rows) of a canvas
+        `height` rows high (z2d_surface_create_band); `self.height` is then the number of rows held."""
         self.backend = backend or default_backend()
         self.format = Format(format)
         if width < 1:
             raise abi.InvalidWidth()
         if height < 1:
             raise abi.InvalidHeight()
-        self.width, self.height = int(width), int(height)
-        self.handle = self.backend.surface_create(self.format, self.width, self.height, initial_px)
+        self.width, self.canvas_height = int(width), int(height)
+        if band is None:
+            self.band_y0, self.height = 0, int(height)
+            self.handle = self.backend.surface_create(self.format, self.width, self.height, initial_px)
+        else:
+            self.band_y0, self.height = int(band[0]), int(band[1])
+            self.handle = self.backend.surface_create_band(self.format, self.width, self.canvas_height, self.band_y0, self.height, initial_px)
 
     @staticmethod
     def init(format, width, height, backend=None):
