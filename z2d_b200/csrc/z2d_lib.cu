@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -130,7 +131,8 @@ struct z2d_ctx {
   std::mutex mu;
   std::condition_variable cv;
   Batch* pending = nullptr;  // batch handed to the worker
-  bool busy = false, stop = false;
+  std::atomic<bool> busy{false};  // written under `mu`; read lock-free by the recorder
+  bool stop = false;
   int async_rc = 0;          // first error of the batches the worker executed since the last wait
 
   // device state
@@ -851,6 +853,7 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
 
 constexpr size_t kMaxBatchNodes = 8u << 20;   // flush thresholds (bounds pinned + device scratch)
 constexpr size_t kMaxBatchDraws = 1u << 20;
+constexpr size_t kMinChunkDraws = 8192;        // smallest batch worth handing to the worker (fixed cost of a batch ~0.3 ms)
 
 }  // namespace
 
@@ -1157,7 +1160,12 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     return rc;
   }
   if (d.mode != 0 || c->rec->nodes.n > kMaxBatchNodes || c->rec->draws.n > kMaxBatchDraws) return flush(c);
-  if (c->chunk_draws && c->rec->draws.n >= c->chunk_draws) return kick(c);  // asynchronous: recording continues
+  // Pipelined recording: hand the batch to the worker as soon as it is idle (so the device starts early and is fed batches as
+  // large as the time it took to execute the previous one), at the latest every chunk_draws draws.  Asynchronous: recording
+  // continues into the other batch.
+  if (c->chunk_draws && c->rec->draws.n >= kMinChunkDraws &&
+      (c->rec->draws.n >= c->chunk_draws || !c->busy.load(std::memory_order_relaxed)))
+    return kick(c);
   return Z2D_OK;
 }
 
