@@ -197,12 +197,12 @@ template <bool EMIT>
 Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint32_t end, double tol, EdgeSink<EMIT>& sink) {
   Pt first{0, 0}, last{0, 0};
   int len = 0;  // PointBuffer(1,3): first point + sliding window; only first/last/len matter
-  auto add_pt = [&](Pt p) {
+  auto add_pt = [&](Pt p) Z2D_LAMBDA {
     if (len == 0) first = p;
     if (len < 3) len++;
     last = p;
   };
-  auto line_to = [&](Pt p) {
+  auto line_to = [&](Pt p) Z2D_LAMBDA {
     if (!pt_eq(last, p)) {
       sink.add(last, p);
       add_pt(p);
@@ -336,7 +336,7 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
   }
   const z2d_node pv = nodes[i - 1];  // move_to, line_to or curve_to
   Pt last = pv.tag == Z2D_NODE_CURVE_TO ? Pt{pv.p[4], pv.p[5]} : Pt{pv.p[0], pv.p[1]};
-  auto line_to = [&](Pt p) {
+  auto line_to = [&](Pt p) Z2D_LAMBDA {
     if (!pt_eq(last, p)) {
       sink.add(last, p);
       last = p;

@@ -19,7 +19,7 @@ namespace z2d {
 Z2D_D RGBA16 mask_mul16(RGBA16 s, int m) { return {iM(s.r, m), iM(s.g, m), iM(s.b, m), iM(s.a, m)}; }  // dst_in(dst:=s, src:=alpha8 m)
 
 // generic StrideCompositor batch: [dst_in(pattern, mask)]? ; op   (shared.zig:24-45, 78-102), any source / precision
-__device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables& T, uint32_t precision, uint32_t fmt, uint32_t raw,
+__device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables T, uint32_t precision, uint32_t fmt, uint32_t raw,
                                                    int mask8, bool use_mask, int x, int y) {
   if (precision == Z2D_PRECISION_INTEGER) {
     RGBA16 s = src_int(d.src, T, x, y, 0);
@@ -151,7 +151,7 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
     if (TWO) p1[k] = ((wl1 >> k) & 1) ? ~0ull : 0ull;
   }
   const int sx_hi = sx0 + ncols;
-  auto apply = [&](const double4& ev, bool up, bool a0, bool a1) {
+  auto apply = [&](const double4& ev, bool up, bool a0, bool a1) Z2D_LAMBDA {
     const double top = up ? ev.y : ev.x;
     n_eval += (uint32_t)a0 + (uint32_t)(TWO && a1);
     if (a0) {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
       const int src_lane = __ffs(hits) - 1;
       hits &= hits - 1;
       const uint32_t di = __shfl_sync(0xffffffffu, it.x, src_lane);
-      const DrawHot h = A.hots[di];
+      const DrawHot& h = A.hots[di];  // read on demand (uniform, L1-resident): keeping all 24 fields live costs more in spills
 
       // ---- coverage
       const int aa = (int)h.aa;

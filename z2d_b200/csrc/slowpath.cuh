@@ -133,13 +133,13 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
   // current contour: only its last point and length matter
   Pt c_last{0, 0};
   uint32_t c_len = 0;
-  auto contour_plot = [&](Pt p) {
+  auto contour_plot = [&](Pt p) Z2D_LAMBDA {
     if (c_len >= 1)
       hl_draw_line(hc, (int)round_half_away(c_last.x), (int)round_half_away(c_last.y), (int)round_half_away(p.x), (int)round_half_away(p.y));
     c_last = p;
     c_len++;
   };
-  auto contour_end = [&]() {  // contour appended to the result list
+  auto contour_end = [&]() Z2D_LAMBDA {  // contour appended to the result list
     if (c_len == 1) hl_opaque(hc, (int)round_half_away(c_last.x), (int)round_half_away(c_last.y));
     c_len = 0;
   };
@@ -147,7 +147,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
   // PointBuffer(1, 2)
   Pt p_first{0, 0}, p_last{0, 0};
   int p_len = 0;
-  auto pts_add = [&](Pt p) {
+  auto pts_add = [&](Pt p) Z2D_LAMBDA {
     if (p_len == 0) p_first = p;
     if (p_len < 2) p_len++;
     p_last = p;
@@ -160,7 +160,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
   int d_idx = 0;
   bool d_on = true;
   double d_remain = 0;
-  auto dash_reset = [&]() {
+  auto dash_reset = [&]() Z2D_LAMBDA {
     d_idx = 0;
     d_on = true;
     d_remain = dd[0];
@@ -176,7 +176,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
       d_on = !d_on;
     }
   };
-  auto dash_step = [&](double len) -> bool {
+  auto dash_step = [&](double len) Z2D_LAMBDA -> bool {
     d_remain -= len;
     if (d_remain <= 0) {
       d_on = !d_on;
@@ -189,7 +189,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
   };
   if (dashed) dash_reset();
 
-  auto dashed_line_to = [&](Pt p0, Pt p1) {  // polyline_plotter.zig:183-221
+  auto dashed_line_to = [&](Pt p0, Pt p1) Z2D_LAMBDA {  // polyline_plotter.zig:183-221
     Slope s{p1.x - p0.x, p1.y - p0.y};
     const double total = slope_normalize(s);
     double remaining = total;
@@ -206,7 +206,7 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
       step = fmin(d_remain, remaining);
     }
   };
-  auto line_to = [&](Pt p) {
+  auto line_to = [&](Pt p) Z2D_LAMBDA {
     if (p_len == 0) return;
     const Pt last = p_last;
     if (pt_eq(last, p)) return;

@@ -164,8 +164,8 @@ Z2D_D void pen_range(const StrokeCtx& c, Slope from, Slope to, bool clockwise, i
   const PenV* v = c.pen;
   const int n = c.npen;
   int start = 0, end = 0;
-  auto cw = [&](int i) { return Slope{v[i].cwx, v[i].cwy}; };
-  auto ccw = [&](int i) { return Slope{v[i].ccwx, v[i].ccwy}; };
+  auto cw = [&](int i) Z2D_LAMBDA { return Slope{v[i].cwx, v[i].cwy}; };
+  auto ccw = [&](int i) Z2D_LAMBDA { return Slope{v[i].ccwx, v[i].ccwy}; };
   if (clockwise) {
     int low = 0, high = n, i = (low + high) >> 1;
     while (high - low > 1) {
@@ -361,12 +361,12 @@ struct Stroker {
     const bool switched = join_cw != poly_cw;
     Block blk;
     blk.active = use_before && st.outer.len > 0;
-    auto plot_outer = [&](Pt p) {
+    auto plot_outer = [&](Pt p) Z2D_LAMBDA {
       if (blk.active) block_push(st.outer, blk, p); else append(st.outer, p);
     };
-    auto plot_inner = [&](Pt p) { prepend(st.inner, p); };
-    auto outer_j = [&](Pt p) { if (switched) plot_inner(p); else plot_outer(p); };
-    auto inner_j = [&](Pt p) { if (switched) plot_outer(p); else plot_inner(p); };
+    auto plot_inner = [&](Pt p) Z2D_LAMBDA { prepend(st.inner, p); };
+    auto outer_j = [&](Pt p) Z2D_LAMBDA { if (switched) plot_inner(p); else plot_outer(p); };
+    auto inner_j = [&](Pt p) Z2D_LAMBDA { if (switched) plot_outer(p); else plot_inner(p); };
 
     if (cmp == 0) {
       outer_j(join_cw ? in.p1_ccw : in.p1_cw);
@@ -405,8 +405,8 @@ struct Stroker {
   Z2D_D void plot_single(PlotState& st, Pt start, Pt end) {  // stroke_plotter.zig:251-294
     const Face f = face_init(start, end, c);
     const Face rev = face_init(end, start, c);  // cap_p0 caps the reversed face
-    cap(rev, true, [&](Pt p) { append(st.outer, p); });
-    cap(f, true, [&](Pt p) { append(st.outer, p); });
+    cap(rev, true, [&](Pt p) Z2D_LAMBDA { append(st.outer, p); });
+    cap(f, true, [&](Pt p) Z2D_LAMBDA { append(st.outer, p); });
     close_contour(st.outer);
     st.clockwise = -1;
   }
@@ -416,14 +416,14 @@ struct Stroker {
     const Face fe = face_init(start1, end1, c);
     const bool cw = st.clockwise >= 0 ? (st.clockwise != 0) : true;
     if (st.outer.len == 0) {
-      cap(fs_rev, cw, [&](Pt p) { append(st.outer, p); });
+      cap(fs_rev, cw, [&](Pt p) Z2D_LAMBDA { append(st.outer, p); });
     } else {
       Block blk;
       blk.active = true;
-      cap(fs_rev, cw, [&](Pt p) { block_push(st.outer, blk, p); });
+      cap(fs_rev, cw, [&](Pt p) Z2D_LAMBDA { block_push(st.outer, blk, p); });
       block_end(st.outer, blk);
     }
-    cap(fe, cw, [&](Pt p) { append(st.outer, p); });
+    cap(fe, cw, [&](Pt p) Z2D_LAMBDA { append(st.outer, p); });
     concat(st.outer, st.inner);
     close_contour(st.outer);
     st.inner.len = 0;
@@ -457,12 +457,12 @@ struct Stroker {
   Z2D_D void run_plain(const z2d_node* __restrict__ nodes, uint32_t begin, uint32_t end) {
     PlotState st;
     PointBuf25 pts;
-    auto line_to = [&](uint32_t join_mode, Pt p) {
+    auto line_to = [&](uint32_t join_mode, Pt p) Z2D_LAMBDA {
       if (pts.len == 0 || pt_eq(p, pts.last())) return;
       pts.add(p);
       if (pts.len > 2) join(st, join_mode, pts.tail(3), pts.tail(2), pts.tail(1), false);
     };
-    auto finish = [&]() {
+    auto finish = [&]() Z2D_LAMBDA {
       if (pts.len == 2) plot_single(st, pts.head(0), pts.head(1));
       else if (pts.len > 2) plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
     };
@@ -477,7 +477,7 @@ struct Stroker {
         case Z2D_NODE_LINE_TO: line_to(c.join, {nd.p[0], nd.p[1]}); break;
         case Z2D_NODE_CURVE_TO:
           if (pts.len == 0) break;
-          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) { line_to(Z2D_JOIN_ROUND, p); });
+          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) Z2D_LAMBDA { line_to(Z2D_JOIN_ROUND, p); });
           break;
         default:  // close_path (stroke_plotter.zig:157-180)
           if (pts.len == 1) {
@@ -559,12 +559,12 @@ struct Stroker {
     Dasher dasher{c.dashes, c.ndash, c.dash_offset, 0, true, 0.0};
     dasher.reset();
 
-    auto emit_current = [&]() {
+    auto emit_current = [&]() Z2D_LAMBDA {
       if (pts.len == 1) plot_dotted_dashed(st, pts.first(), cur_slope);
       else if (pts.len == 2) plot_single(st, pts.head(0), pts.head(1));
       else if (pts.len > 2) plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
     };
-    auto save_initial = [&]() {  // 467-520
+    auto save_initial = [&]() Z2D_LAMBDA {  // 467-520
       if (!dasher.on) {
         initial_kind = 2;
         ist = st;
@@ -578,13 +578,13 @@ struct Stroker {
       st.inner.len = 0;
       st.clockwise = -1;
     };
-    auto next_segment = [&](Pt point) {  // 307-332
+    auto next_segment = [&](Pt point) Z2D_LAMBDA {  // 307-332
       if (initial_kind == 0) save_initial();
       else if (!dasher.on) emit_current();
       pts.reset();
       pts.add(point);
     };
-    auto finish_initial = [&]() {  // finishInitialDotted / finishInitial (522-552)
+    auto finish_initial = [&]() Z2D_LAMBDA {  // finishInitialDotted / finishInitial (522-552)
       if (ipts.len == 1) {
         plot_dotted_dashed(st, ipts.first(), islope);
       } else if (ipts.len >= 2) {
@@ -592,7 +592,7 @@ struct Stroker {
       }
       initial_kind = 0;
     };
-    auto line_to = [&](uint32_t join_mode, Pt target) {  // _runLineTo (123-173)
+    auto line_to = [&](uint32_t join_mode, Pt target) Z2D_LAMBDA {  // _runLineTo (123-173)
       if (pts.len == 0) return;
       const Pt current = pts.last();
       if (pt_eq(target, current)) return;
@@ -615,7 +615,7 @@ struct Stroker {
         step_len = fmin(dasher.remain, remaining);
       }
     };
-    auto finish = [&]() {  // 334-367
+    auto finish = [&]() Z2D_LAMBDA {  // 334-367
       if (initial_kind == 2) {
         if (ipts.len >= 1) finish_initial();
       } else if (initial_kind == 1) {
@@ -623,7 +623,7 @@ struct Stroker {
       }
       if (dasher.on) emit_current();
     };
-    auto join_and_cap_initial = [&]() {  // 554-628
+    auto join_and_cap_initial = [&]() Z2D_LAMBDA {  // 554-628
       if (pts.len > 2) {
         join(st, c.join, pts.tail(2), ipts.head(0), ipts.head(1), false);
         concat(st.outer, ist.outer);  // self.outer.concat(&initial.outer)
@@ -652,7 +652,7 @@ struct Stroker {
         case Z2D_NODE_LINE_TO: line_to(c.join, {nd.p[0], nd.p[1]}); break;
         case Z2D_NODE_CURVE_TO:
           if (pts.len == 0) break;
-          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) { line_to(Z2D_JOIN_ROUND, p); });
+          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) Z2D_LAMBDA { line_to(Z2D_JOIN_ROUND, p); });
           break;
         default: {  // close_path (202-305)
           if (pts.len == 0) break;
