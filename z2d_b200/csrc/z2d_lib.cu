@@ -92,6 +92,7 @@ struct z2d_sfc {
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
   uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0;
+  int set = 0;  // which InputSet holds the batch
   size_t n_nodes = 0, h2d_bytes = 0;
 };
 
@@ -100,6 +101,7 @@ struct Batch {  // one recorded command batch (host side)
   PinnedVec<z2d_node> nodes;
   PinnedVec<DevSubPath> subpaths;
   PinnedVec<DrawIn> draws;
+  PinnedVec<uint8_t> side;        // pinned staging of the side tables (built at flush)
   std::vector<StrokeIn> strokes;  // side tables of the batch
   std::vector<DevSrc> srcs;
   uint32_t iso_mode = 0, iso_node_begin = 0, iso_node_end = 0;  // the isolated draw of a 1-draw batch
@@ -113,6 +115,28 @@ struct Batch {  // one recorded command batch (host side)
   double pen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // parameters of the most recently built pen (thickness, tolerance, ctm)
   uint32_t pen_last_begin = 0, pen_last_count = 0;
   bool pen_cached = false;
+};
+
+struct InputSet {  // device copies of one batch's uploaded inputs; two sets, so that the upload of batch k+1 (copy stream)
+                   // overlaps the kernels of batch k (which read the other set)
+  DevBuf d_nodes, d_subpaths, d_draws_in;
+  DevBuf d_side;  // all small tables of the batch, packed into one pinned blob on the host and uploaded with one copy
+  const StrokeIn* strokes = nullptr;
+  const DevSrc* srcs = nullptr;
+  const DevSurface* sfcs = nullptr;
+  const uint32_t* work_base = nullptr;
+  const uint32_t* chunk_base = nullptr;
+  const DevGrad* grads = nullptr;
+  const float* stop_off = nullptr;
+  const float4* stop_col = nullptr;
+  const void* pens = nullptr;
+  const double* dashes = nullptr;
+  cudaEvent_t done = nullptr;  // recorded on the main stream after the last kernel that reads this set
+  bool used = false;
+  void release() {
+    DevBuf* b[] = {&d_nodes, &d_subpaths, &d_draws_in, &d_side};
+    for (DevBuf* x : b) x->release();
+  }
 };
 
 struct z2d_ctx {
@@ -136,9 +160,11 @@ struct z2d_ctx {
   int async_rc = 0;          // first error of the batches the worker executed since the last wait
 
   // device state
-  DevBuf d_pens, d_dashes;
-  DevBuf d_draws_in, d_strokes, d_srcs, d_node_sp, d_chunk_base, d_curve_list;
-  DevBuf d_blue, d_nodes, d_subpaths, d_draws, d_sfcs, d_grads, d_stop_off, d_stop_col, d_work_base;
+  InputSet in[2];
+  cudaStream_t copy_stream = nullptr;  // H2D of batch inputs
+  cudaEvent_t ev_up = nullptr;
+  DevBuf d_node_sp, d_curve_list;
+  DevBuf d_blue, d_draws;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
   DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
@@ -437,6 +463,15 @@ void clear_batch(z2d_ctx* c, Batch& B) {
   B.pen_cached = false;
 }
 
+GradTables tables(z2d_ctx* c, const DevGrad* g, const float* so, const float4* sc) {
+  GradTables T;
+  T.grads = g;
+  T.stop_offsets = so;
+  T.stop_colors = sc;
+  T.blue_noise = c->d_blue.as<uint16_t>();
+  return T;
+}
+
 GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& sc) {
   GradTables T;
   T.grads = g.as<DevGrad>();
@@ -451,6 +486,7 @@ GradTables tables(z2d_ctx* c, const DevBuf& g, const DevBuf& so, const DevBuf& s
 int run_pipeline(z2d_ctx* c, bool replay) {
   const BatchMeta& m = c->last;
   if (!m.valid || m.n_draws == 0) return Z2D_OK;
+  InputSet& S = c->in[m.set];
   cudaStream_t st = c->stream;
   const uint32_t n_draws = m.n_draws, n_sp = m.n_sp, n_sfc = m.n_sfc, n_work = m.n_work;
   uint32_t launches = 0;
@@ -466,7 +502,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, c->d_counters.ensure(64));
   CK(c, cudaMemsetAsync(c->d_counters.p, 0, 64, st));
   CK(c, cudaEventRecord(c->ev[0], st));
-  launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), n_draws, st);
+  launch_expand_draws(S.d_draws_in.as<DrawIn>(), S.strokes, S.srcs, c->d_draws.as<DevDraw>(), n_draws, st);
 
   // K1: flatten (count, scan, emit).  Count slots: one per sub-path (sequential plotters: strokes, irregular fills) followed,
   // when the batch has node-parallel sub-paths, by one per node.
@@ -474,12 +510,12 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   const bool par = m.n_par_sp != 0;
   const uint32_t n_cnt = n_sp + (par ? n_nodes : 0u);
   CK(c, c->d_sp_count.ensure((size_t)n_cnt * 4 + 16));
-  launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
-                       c->d_pens.p, c->d_dashes.as<double>(), st);
+  launch_flatten_count(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
+                       S.pens, S.dashes, st);
   if (par) {
     CK(c, c->d_node_sp.ensure((size_t)n_nodes * 4 + 16));
     CK(c, c->d_curve_list.ensure(((size_t)n_nodes + 1) * 4 + 16));
-    launch_flatten_nodes(false, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
+    launch_flatten_nodes(false, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
                          c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr,
                          c->d_curve_list.as<uint32_t>(), st);
     launches += 5;
@@ -492,10 +528,10 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   }
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
-  launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
+  launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
+                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, st);
   if (par) {
-    launch_flatten_nodes(true, c->d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, c->d_nodes.as<z2d_node>(),
+    launch_flatten_nodes(true, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
                          c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
                          c->d_edge_draw.as<uint32_t>(), c->d_curve_list.as<uint32_t>(), st);
     launches += 2;
@@ -506,7 +542,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
   CK(c, c->d_boxes.ensure((size_t)n_draws * sizeof(DrawBox) + 16));
   CK(c, c->d_hots.ensure((size_t)n_draws * sizeof(DrawHot) + 16));
-  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, c->d_sfcs.as<DevSurface>(), c->d_draw_bands.as<uint32_t>(), c->d_boxes.as<DrawBox>(),
+  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, c->d_draw_bands.as<uint32_t>(), c->d_boxes.as<DrawBox>(),
                      c->d_counters.as<unsigned long long>(), st);
   CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
   uint32_t n_slots = 0;
@@ -536,7 +572,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 
   // K3b: ordered draw list per surface tile-row
   CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
-  launch_band_lists(false, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), c->d_chunk_base.as<uint32_t>(), m.n_chunks,
+  launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
                     c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
   uint32_t n_items = 0;
@@ -545,16 +581,16 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     if (rc) return rc;
   }
   CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
-  launch_band_lists(true, c->d_sfcs.as<DevSurface>(), n_sfc, c->d_work_base.as<uint32_t>(), c->d_chunk_base.as<uint32_t>(), m.n_chunks,
+  launch_band_lists(true, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
                     c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
   // K4: fused coverage + compositing
   RasterArgs A;
-  A.sfcs = c->d_sfcs.as<DevSurface>();
+  A.sfcs = S.sfcs;
   A.n_sfc = n_sfc;
   A.n_tiles = m.n_tiles;
-  A.work_base = c->d_work_base.as<uint32_t>();
+  A.work_base = S.work_base;
   A.list_off = c->d_list_off.as<uint32_t>();
   A.list_items = c->d_list_items.as<uint2>();
   A.draws = c->d_draws.as<DevDraw>();
@@ -563,7 +599,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.band_edges = c->d_band_edges.as<DevEdge>();
   A.band_hdr = c->d_band_hdr.as<int4>();
   A.counters = c->d_counters.as<unsigned long long>();
-  A.T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
+  A.T = tables(c, S.grads, S.stop_off, S.stop_col);
   launch_raster(A, st);
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev[4], st));
@@ -587,20 +623,21 @@ int run_pipeline(z2d_ctx* c, bool replay) {
 // (slowpath.cuh); they run as a batch of exactly one draw.
 int run_isolated(z2d_ctx* c, Batch& B) {
   const BatchMeta& m = c->last;
+  InputSet& S = c->in[m.set];
   cudaStream_t st = c->stream;
-  const GradTables T = tables(c, c->d_grads, c->d_stop_off, c->d_stop_col);
+  const GradTables T = tables(c, S.grads, S.stop_off, S.stop_col);
   uint32_t launches = 0, n_edges = 0;
   CK(c, cudaEventRecord(c->ev[0], st));
-  launch_expand_draws(c->d_draws_in.as<DrawIn>(), c->d_strokes.as<StrokeIn>(), c->d_srcs.as<DevSrc>(), c->d_draws.as<DevDraw>(), 1, st);
+  launch_expand_draws(S.d_draws_in.as<DrawIn>(), S.strokes, S.srcs, c->d_draws.as<DevDraw>(), 1, st);
   if (B.iso_mode == 1) {
-    launch_hairline(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_nodes.as<z2d_node>(), B.iso_node_begin, B.iso_node_end,
-                    c->d_dashes.as<double>(), T, st);
+    launch_hairline(S.sfcs, c->d_draws.as<DevDraw>(), 0, S.d_nodes.as<z2d_node>(), B.iso_node_begin, B.iso_node_end,
+                    S.dashes, T, st);
     launches = 2;
   } else {
     const uint32_t n_sp = m.n_sp;
     CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
-    launch_flatten_count(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
-                         c->d_pens.p, c->d_dashes.as<double>(), st);
+    launch_flatten_count(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
+                         S.pens, S.dashes, st);
     CK(c, c->d_sp_off.ensure(((size_t)n_sp + 1) * 4));
     CK(c, c->d_scan_tmp.ensure(scan_tmp_len(n_sp) * 4));
     exclusive_scan(c->d_sp_count.as<uint32_t>(), c->d_sp_off.as<uint32_t>(), n_sp, c->d_scan_tmp.as<uint32_t>(), st);
@@ -608,9 +645,9 @@ int run_isolated(z2d_ctx* c, Batch& B) {
     if (rc) return rc;
     CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
     CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
-    launch_flatten_emit(c->d_subpaths.as<DevSubPath>(), n_sp, c->d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->d_pens.p, c->d_dashes.as<double>(), st);
-    launch_direct_unbounded(c->d_sfcs.as<DevSurface>(), c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, B.batch_sfcs[0]->h, T, st);
+    launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
+                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, st);
+    launch_direct_unbounded(S.sfcs, c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, B.batch_sfcs[0]->h, T, st);
     launches = 7;
   }
   CK(c, cudaGetLastError());
@@ -686,23 +723,56 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   const uint32_t n_work = work_base[n_sfc];
   const uint32_t n_sp = (uint32_t)B.subpaths.n;
 
-  // 2. upload the batch
-  CK(c, upload(c, c->d_nodes, B.nodes.p, B.nodes.n * sizeof(z2d_node)));
-  CK(c, upload(c, c->d_subpaths, B.subpaths.p, B.subpaths.n * sizeof(DevSubPath)));
-  CK(c, upload(c, c->d_draws_in, B.draws.p, B.draws.n * sizeof(DrawIn)));
-  CK(c, upload(c, c->d_strokes, B.strokes.data(), B.strokes.size() * sizeof(StrokeIn)));
-  CK(c, upload(c, c->d_srcs, B.srcs.data(), B.srcs.size() * sizeof(DevSrc)));
+  // 2. upload the batch on the copy stream into this batch's input set, so that the transfer overlaps the kernels of the
+  //    previous batch (which read the other set); the set is free once the last batch that used it has passed its raster kernel.
+  //    The small tables travel as one pinned blob (sections 256-byte aligned) with typed device pointers into it.
+  InputSet& S = c->in[B.index];
+  struct Sec { const void* src; size_t bytes; size_t off; };
+  Sec sec[10] = {{B.strokes.data(), B.strokes.size() * sizeof(StrokeIn), 0}, {B.srcs.data(), B.srcs.size() * sizeof(DevSrc), 0},
+                 {sfcs.data(), sfcs.size() * sizeof(DevSurface), 0},         {work_base.data(), work_base.size() * 4, 0},
+                 {chunk_base.data(), chunk_base.size() * 4, 0},             {B.grads.data(), B.grads.size() * sizeof(DevGrad), 0},
+                 {B.stop_offsets.data(), B.stop_offsets.size() * 4, 0},     {B.stop_colors.data(), B.stop_colors.size() * sizeof(float4), 0},
+                 {B.pens.data(), B.pens.size() * 8, 0},                     {B.dashes.data(), B.dashes.size() * 8, 0}};
+  size_t side_bytes = 0;
+  for (Sec& x : sec) {
+    x.off = side_bytes;
+    side_bytes += (x.bytes + 255) & ~(size_t)255;
+  }
+  side_bytes += 256;
+  if (!B.side.reserve(side_bytes)) return Z2D_E_OUT_OF_MEMORY;
+  for (const Sec& x : sec)
+    if (x.bytes) memcpy(B.side.p + x.off, x.src, x.bytes);
+  CK(c, S.d_nodes.ensure(B.nodes.n * sizeof(z2d_node) + 16));
+  CK(c, S.d_subpaths.ensure(B.subpaths.n * sizeof(DevSubPath) + 16));
+  CK(c, S.d_draws_in.ensure(B.draws.n * sizeof(DrawIn) + 16));
+  CK(c, S.d_side.ensure(side_bytes));
   CK(c, c->d_draws.ensure(B.draws.n * sizeof(DevDraw)));
-  CK(c, upload(c, c->d_sfcs, sfcs.data(), sfcs.size() * sizeof(DevSurface)));
-  CK(c, upload(c, c->d_work_base, work_base.data(), work_base.size() * 4));
-  CK(c, upload(c, c->d_chunk_base, chunk_base.data(), chunk_base.size() * 4));
-  CK(c, upload(c, c->d_grads, B.grads.data(), B.grads.size() * sizeof(DevGrad)));
-  CK(c, upload(c, c->d_stop_off, B.stop_offsets.data(), B.stop_offsets.size() * 4));
-  CK(c, upload(c, c->d_stop_col, B.stop_colors.data(), B.stop_colors.size() * sizeof(float4)));
-  CK(c, upload(c, c->d_pens, B.pens.data(), B.pens.size() * 8));
-  CK(c, upload(c, c->d_dashes, B.dashes.data(), B.dashes.size() * 8));
+  if (S.used) CK(c, cudaStreamWaitEvent(c->copy_stream, S.done, 0));
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    return bytes ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->copy_stream) : cudaSuccess;
+  };
+  CK(c, up(S.d_nodes, B.nodes.p, B.nodes.n * sizeof(z2d_node)));
+  CK(c, up(S.d_subpaths, B.subpaths.p, B.subpaths.n * sizeof(DevSubPath)));
+  CK(c, up(S.d_draws_in, B.draws.p, B.draws.n * sizeof(DrawIn)));
+  CK(c, up(S.d_side, B.side.p, side_bytes));
+  {
+    const uint8_t* base = S.d_side.as<uint8_t>();
+    S.strokes = reinterpret_cast<const StrokeIn*>(base + sec[0].off);
+    S.srcs = reinterpret_cast<const DevSrc*>(base + sec[1].off);
+    S.sfcs = reinterpret_cast<const DevSurface*>(base + sec[2].off);
+    S.work_base = reinterpret_cast<const uint32_t*>(base + sec[3].off);
+    S.chunk_base = reinterpret_cast<const uint32_t*>(base + sec[4].off);
+    S.grads = reinterpret_cast<const DevGrad*>(base + sec[5].off);
+    S.stop_off = reinterpret_cast<const float*>(base + sec[6].off);
+    S.stop_col = reinterpret_cast<const float4*>(base + sec[7].off);
+    S.pens = base + sec[8].off;
+    S.dashes = reinterpret_cast<const double*>(base + sec[9].off);
+  }
+  CK(c, cudaEventRecord(c->ev_up, c->copy_stream));
+  CK(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0));
   BatchMeta& m = c->last;
   m.valid = true;
+  m.set = B.index;
   m.n_draws = n_draws;
   m.n_sp = n_sp;
   m.n_par_sp = B.n_par_sp;
@@ -716,6 +786,8 @@ int flush_impl(z2d_ctx* c, Batch& B) {
                 sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + B.grads.size() * sizeof(DevGrad) +
                 B.stop_offsets.size() * 4 + B.stop_colors.size() * sizeof(float4);
   int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) != 0) ? run_isolated(c, B) : run_pipeline(c, false);
+  cudaEventRecord(S.done, c->stream);  // (also on failure: the set is reusable after whatever was enqueued)
+  S.used = true;
   clear_batch(c, B);
   return rc;
 }
@@ -883,6 +955,9 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   for (auto& e : c->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
+  for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
       cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
     delete c;
@@ -907,16 +982,22 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   cudaStreamSynchronize(c->stream);
   clear_batch(c, c->bat[0]);
   clear_batch(c, c->bat[1]);
-  DevBuf* bufs[] = {&c->d_blue, &c->d_nodes, &c->d_subpaths, &c->d_draws, &c->d_sfcs, &c->d_grads, &c->d_stop_off, &c->d_stop_col,
-                    &c->d_work_base, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands, &c->d_draw_band_off,
-                    &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt, &c->d_list_off, &c->d_list_items,
-                    &c->d_scan_tmp, &c->d_pens, &c->d_dashes, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
-                    &c->d_draws_in, &c->d_strokes, &c->d_srcs, &c->d_node_sp, &c->d_chunk_base, &c->d_curve_list};
+  DevBuf* bufs[] = {&c->d_blue, &c->d_draws, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands,
+                    &c->d_draw_band_off, &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt,
+                    &c->d_list_off, &c->d_list_items, &c->d_scan_tmp, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
+                    &c->d_node_sp, &c->d_curve_list};
   for (DevBuf* b : bufs) b->release();
+  for (InputSet& is : c->in) {
+    is.release();
+    if (is.done) cudaEventDestroy(is.done);
+  }
+  if (c->ev_up) cudaEventDestroy(c->ev_up);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (Batch& b : c->bat) {
     b.nodes.release();
     b.subpaths.release();
     b.draws.release();
+    b.side.release();
   }
   if (c->h_total) cudaFreeHost(c->h_total);
   c->d_counters.release();
