@@ -521,13 +521,32 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     launches += 5;
   }
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
-  uint32_t n_edges = 0;
-  {
-    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_cnt, n_edges);
-    if (rc) return rc;
-  }
+
+  // K2: per-draw regions and (draw, tile-row) slots; K3b (count half): sizes of the per-tile-row draw lists.  Both only need
+  // the extents gathered by the count pass, so they run before the edges exist and the three totals the host needs for
+  // allocation come back in ONE round trip.
+  CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
+  CK(c, c->d_boxes.ensure((size_t)n_draws * sizeof(DrawBox) + 16));
+  CK(c, c->d_hots.ensure((size_t)n_draws * sizeof(DrawHot) + 16));
+  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, c->d_draw_bands.as<uint32_t>(), c->d_boxes.as<DrawBox>(),
+                     c->d_counters.as<unsigned long long>(), st);
+  CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
+  CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
+  launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
+                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
+  CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
+  CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + n_cnt, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(c->h_total + 2, c->d_list_off.as<uint32_t>() + n_work, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  const uint32_t n_edges = c->h_total[0], n_slots = c->h_total[1], n_items = c->h_total[2];
+
+  // K1 (emit half)
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
+  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
+  CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
+  CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
   launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
                       c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, st);
   if (par) {
@@ -538,23 +557,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   }
   CK(c, cudaEventRecord(c->ev[1], st));
 
-  // K2: per-draw regions; (draw, tile-row) slots
-  CK(c, c->d_draw_bands.ensure((size_t)n_draws * 4 + 16));
-  CK(c, c->d_boxes.ensure((size_t)n_draws * sizeof(DrawBox) + 16));
-  CK(c, c->d_hots.ensure((size_t)n_draws * sizeof(DrawHot) + 16));
-  launch_setup_draws(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, c->d_draw_bands.as<uint32_t>(), c->d_boxes.as<DrawBox>(),
-                     c->d_counters.as<unsigned long long>(), st);
-  CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
-  uint32_t n_slots = 0;
-  {
-    int rc = read_total(c, c->d_draw_band_off.as<uint32_t>() + n_draws, n_slots);
-    if (rc) return rc;
-  }
-  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), st);
-
   // K3a: edges -> (draw, tile-row) lists
-  CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
-  CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
+  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), st);
   CK(c, cudaMemsetAsync(c->d_band_count.p, 0, (size_t)n_slots * 4 + 16, st));
   CK(c, cudaMemsetAsync(c->d_band_cursor.p, 0, (size_t)n_slots * 4 + 16, st));
   launch_bin_count(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_count.as<uint32_t>(), st);
@@ -570,17 +574,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
                      c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), c->d_band_hdr.as<int4>(), st);
   CK(c, cudaEventRecord(c->ev[2], st));
 
-  // K3b: ordered draw list per surface tile-row
-  CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
-  launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
-                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
-  CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
-  uint32_t n_items = 0;
-  {
-    int rc = read_total(c, c->d_list_off.as<uint32_t>() + n_work, n_items);
-    if (rc) return rc;
-  }
-  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
+  // K3b (write half): ordered draw list per surface tile-row
   launch_band_lists(true, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
                     c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
