@@ -37,6 +37,19 @@ METRIC = "filled+composited Mpix/s"
 UNIT = "Mpix/s"
 
 
+def ncu_traffic(kernel_tag):
+    """DRAM bytes per launch of a kernel from the newest committed ncu --set full summary (profiles/*_<tag>_ncu.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"*_{kernel_tag}_ncu.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        return float(d["derived"]["dram_bytes"]), os.path.basename(files[-1])
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -281,7 +294,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int((st["kernel_launches"] + 1) * steps),
             "clocks": clocks,
             "roofline": {"kernel": "k_raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "ms": r_ms,
+                         "frac": achieved / peak, "traffic": ncu_traffic("raster")[0], "traffic_source": ncu_traffic("raster")[1],
+                         "peak_kind": peak_kind, "ms": r_ms,
                          "algorithmic_bytes": algo_bytes,
                          "note": "algorithmic = 8 B per composited pixel (read+write RGBA8 per path, SURVEY 8d) + 32 B per binned edge; "
                                  "the tile-resident design touches each canvas tile once per batch, so DRAM traffic is far below this"},
@@ -327,7 +341,8 @@ def composite_roofline(cb, args):
     sfc.deinit()
     return {"kernel": "k_composite_fast<integer, pixel source>", "workload": "8192x8192 RGBA8 src_over, single-pixel source (BASELINE config 4 shape)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "ms": ms,
-            "mpix_per_s": n * n / (ms * 1e-3) / 1e6, "peak_kind": kind}
+            "mpix_per_s": n * n / (ms * 1e-3) / 1e6, "peak_kind": kind, "traffic": ncu_traffic("composite")[0],
+            "traffic_source": ncu_traffic("composite")[1], "algorithmic_bytes": 8.0 * n * n}
 
 
 def main():

@@ -54,4 +54,4 @@ if __name__ == "__main__":
     cpu_us, _, _ = bench(OracleBackend(fast=True), 50)
     print(json.dumps({"workload": "spec/080_fill_z2d_logo (BASELINE config 1): 601x172 RGBA8, 5 fills, default AA, node lists prebuilt",
                       "fills_per_scene": calls, "nodes_per_scene": nodes, "gpu_us_per_scene": gpu_us, "cpu_oracle_us_per_scene": cpu_us,
-                      "note": "one batch per scene: fixed cost of a batch (uploads, ~27 launches, 4 count read-backs) dominates"}))
+                      "note": "one batch per scene: fixed cost of a batch (uploads, ~27 launches, 2 count read-backs) dominates"}))
