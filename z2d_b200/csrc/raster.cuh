@@ -525,10 +525,10 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           const uint2 sfull = st[16];
           if (lo == 0 && hi == 8 && cov_e == full * 0x01010101u && cov_o == cov_e) {  // interior: all 8 pixels fully covered
             n_cov += 8;
-#pragma unroll
+#pragma unroll 1  // rolled on purpose: the kernel is instruction-fetch bound, 8 unrolled copies of the blend cost more than the loop
             for (int i = 0; i < 8; i++) w[i] = h.reduces ? h.paint_raw : src_over_x4(w[i], sfull, amask);
           } else {
-#pragma unroll
+#pragma unroll 1  // rolled on purpose: the kernel is instruction-fetch bound, 8 unrolled copies of the blend cost more than the loop
             for (int i = 0; i < 8; i++) {
               const uint32_t cov = (((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xffu;
               if (cov == 0 || i < lo || i >= hi) continue;
