@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         continue;
       }
       const DevDraw& d = A.draws[di];
+#pragma unroll 1  // one copy of the generic compositor (28 operators x sources x formats) instead of eight
       for (int i = 0; i < 8; i++) {
         const int x = px0 + i;
         const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
