@@ -58,14 +58,41 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (nvidia-smi's
+    fastest loop, 100 ms, is too coarse for a region of tens of milliseconds); nvidia-smi only as a fallback."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.lines = []
+        self.index, self.sm, self.mx, self.mask = index, [], 0.0, 0
+        self.stop_flag, self.thread, self.proc, self.lines = False, None, None, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML wants the physical one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -80,8 +107,14 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx or None, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -98,7 +131,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def oracle_lib(fast=True):
@@ -348,7 +381,7 @@ def composite_roofline(cb, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=100_000)
