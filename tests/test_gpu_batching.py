@@ -75,3 +75,41 @@ def test_interleaved_surfaces_keep_per_surface_order(cuda):
         ref_sfc.deinit()
     a.deinit()
     b.deinit()
+
+
+def test_parallel_recorder_equals_one_by_one_calls(cuda):
+    """z2d_submit records long runs of plain fills with several host threads; statuses and pixels must equal issuing the same
+    calls one by one through z2d_fill -- including calls that fail (unclosed path, non-premultiplied source) or record
+    nothing (empty node list)."""
+    size, n = 320, 5000
+    scene = workloads.cubic_paths_scene(n, size, seed=0x5EED0004, r_log2=(2.0, 5.0))
+    a = Surface(abi.Format.rgba, size, size, None, cuda)
+    cmds = scene.draw_cmds(a.handle)
+    # break some calls
+    scene.nodes["tag"][scene.node_off[7] + 5] = int(abi.NodeTag.line_to)     # close_path -> line_to: PathNotClosed
+    scene.patterns["pixel"]["r"][11] = 255                                   # r > a: not premultiplied
+    scene.patterns["pixel"]["a"][11] = 10
+    cmds["n_nodes"][13] = 0                                                  # empty node list: silent no-op
+    scene.nodes["tag"][scene.node_off[17]] = int(abi.NodeTag.line_to)        # line_to without a current point: InvalidState
+    statuses = np.zeros(n, dtype=np.int32)
+    rc = cuda.lib.z2d_submit(cuda.ctx, cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), n, statuses.ctypes.data_as(C.POINTER(C.c_int32)))
+    got = a.download().copy()
+    assert rc == abi.E_PATH_NOT_CLOSED  # the first failing call
+    assert statuses[7] == abi.E_PATH_NOT_CLOSED and statuses[11] == abi.E_PIXEL_SOURCE_NOT_PREMULTIPLIED
+    assert statuses[13] == abi.OK and statuses[17] == abi.E_INVALID_STATE
+    assert int((statuses != 0).sum()) == 3
+    # the same calls one by one
+    b = Surface(abi.Format.rgba, size, size, None, cuda)
+    c2 = scene.draw_cmds(b.handle)
+    c2["n_nodes"][13] = 0
+    P = C.POINTER
+    ref_status = []
+    for i in range(n):
+        ref_status.append(cuda.lib.z2d_fill(cuda.ctx, b.handle, C.cast(C.c_void_p(int(c2["pattern"][i])), P(abi.PatternPOD)),
+                                            C.cast(C.c_void_p(int(c2["nodes"][i])), P(abi.Node)), int(c2["n_nodes"][i]),
+                                            C.cast(C.c_void_p(int(c2["fill"][i])), P(abi.FillOptsPOD))))
+    ref = b.download()
+    assert list(statuses) == ref_status
+    assert np.array_equal(got, ref)
+    a.deinit()
+    b.deinit()

@@ -96,6 +96,14 @@ struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_r
   size_t n_nodes = 0, h2d_bytes = 0;
 };
 
+// one call of a run handled by the parallel recorder (z2d_submit)
+struct FillPlan {
+  int32_t status;
+  uint32_t eligible, skip;  // skip: valid call that records nothing (empty node list)
+  uint32_t first, m, n_sp, n_par;
+  uint32_t node_base, sp_base, draw_idx, slot;
+};
+
 struct Batch {  // one recorded command batch (host side)
   int index = 0;
   PinnedVec<z2d_node> nodes;
@@ -150,7 +158,9 @@ struct z2d_ctx {
   // recorded batches: the application thread records into `rec` while the worker may be executing the other one
   Batch bat[2];
   Batch* rec = &bat[0];
-  uint32_t chunk_draws = 32768;  // hand the recording batch to the worker every this many draws (0: never)
+  uint32_t chunk_draws = 32768;
+  unsigned record_threads = 4;          // host threads z2d_submit may use for long runs of plain fills
+  std::vector<FillPlan> fill_plans;     // scratch of the parallel recorder  // hand the recording batch to the worker every this many draws (0: never)
   std::thread worker;
   std::mutex mu;
   std::condition_variable cv;
@@ -867,25 +877,17 @@ bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23
   return closed;
 }
 
-// Split the node list at every move_to and append nodes + sub-path records to the batch.
-int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n, bool allow_parallel) {
-  // leading nodes before the first move_to: line_to / curve_to have no current point
-  // (fill_plotter.zig:50,53 -> InternalError.InvalidState); a leading close_path is a no-op.
-  size_t first = 0;
-  while (first < n && nodes[first].tag != Z2D_NODE_MOVE_TO) {
-    if (nodes[first].tag == Z2D_NODE_LINE_TO || nodes[first].tag == Z2D_NODE_CURVE_TO) return Z2D_E_INVALID_STATE;
-    if (nodes[first].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
-    first++;
-  }
-  const uint32_t base = (uint32_t)c->rec->nodes.n;
-  if (!c->rec->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
-  const size_t m = n - first;
+// Split a node list that starts at a move_to into sub-paths (one per move_to; a lone move_to draws nothing).  out == nullptr:
+// count only.  Flags sub-paths eligible for node-parallel flattening (kSpNodeParallel): move_to, segments..., one close_path
+// at the very end, and at least two segments whose end differs from their start (then the plotter holds >= 3 points at the
+// close, fill_plotter.zig:82).
+int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_index, bool allow_parallel, DevSubPath* out, uint32_t& n_sp,
+                   uint32_t& n_par) {
+  n_sp = 0;
+  n_par = 0;
   size_t i = 0;
   while (i < m) {
     size_t j = i + 1;
-    // node-parallel flattening (kSpNodeParallel): move_to, segments..., one close_path at the very end, and at least two
-    // segments whose end differs from their start (then the plotter holds >= 3 points at the close, fill_plotter.zig:82)
-    const z2d_node* q = nodes + first;
     double cx = q[i].p[0], cy = q[i].p[1];
     int moving = 0;
     bool simple = allow_parallel;
@@ -903,17 +905,42 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
       j++;
     }
     simple = simple && q[j - 1].tag == Z2D_NODE_CLOSE_PATH && moving >= 2;
-    DevSubPath sp;
-    sp.draw = draw_index;
-    sp.node_begin = base + (uint32_t)i;
-    sp.node_end = base + (uint32_t)j;
-    sp.flags = ((j == m) ? kSpLastOfDraw : 0u) | (simple ? kSpNodeParallel : 0u);
-    if (j - i > 1) {  // a lone move_to draws nothing
-      if (!c->rec->subpaths.push(sp)) return Z2D_E_OUT_OF_MEMORY;
-      c->rec->n_par_sp += simple ? 1u : 0u;
+    if (j - i > 1) {
+      if (out) {
+        DevSubPath sp;
+        sp.draw = draw_index;
+        sp.node_begin = base + (uint32_t)i;
+        sp.node_end = base + (uint32_t)j;
+        sp.flags = ((j == m) ? kSpLastOfDraw : 0u) | (simple ? kSpNodeParallel : 0u);
+        out[n_sp] = sp;
+      }
+      n_sp++;
+      n_par += simple ? 1u : 0u;
     }
     i = j;
   }
+  return Z2D_OK;
+}
+
+// Split the node list at every move_to and append nodes + sub-path records to the batch.
+int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n, bool allow_parallel) {
+  // leading nodes before the first move_to: line_to / curve_to have no current point
+  // (fill_plotter.zig:50,53 -> InternalError.InvalidState); a leading close_path is a no-op.
+  size_t first = 0;
+  while (first < n && nodes[first].tag != Z2D_NODE_MOVE_TO) {
+    if (nodes[first].tag == Z2D_NODE_LINE_TO || nodes[first].tag == Z2D_NODE_CURVE_TO) return Z2D_E_INVALID_STATE;
+    if (nodes[first].tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
+    first++;
+  }
+  const uint32_t base = (uint32_t)c->rec->nodes.n;
+  if (!c->rec->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
+  uint32_t n_sp = 0, n_par = 0;
+  int rc = split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, nullptr, n_sp, n_par);
+  if (rc) return rc;
+  if (!c->rec->subpaths.reserve(c->rec->subpaths.n + n_sp)) return Z2D_E_OUT_OF_MEMORY;
+  split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, c->rec->subpaths.p + c->rec->subpaths.n, n_sp, n_par);
+  c->rec->subpaths.n += n_sp;
+  c->rec->n_par_sp += n_par;
   return Z2D_OK;
 }
 
@@ -938,6 +965,15 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   z2d_ctx* c = new z2d_ctx();
   c->device = device;
   c->bat[1].index = 1;
+  {
+    // share the host cores with the other ranks of a torchrun launch (LOCAL_WORLD_SIZE processes on this node)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const char* env = getenv("Z2D_RECORD_THREADS");
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    const unsigned ranks = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
+    c->record_threads = env ? (unsigned)atoi(env) : std::min(4u, hw / (2u * ranks));
+    if (c->record_threads < 1) c->record_threads = 1;
+  }
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
@@ -1383,15 +1419,158 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   return rc;
 }
 
+}  // extern "C"
+
+// ---- parallel recording of runs of plain fills (single-pixel source, tile pipeline): recording is memory bound
+// (~0.9 KB read + written per call), so several host threads split a run.  Three phases: (1) every call is validated and
+// sized in parallel, (2) a serial prefix sum assigns node / sub-path / draw positions (so the batch is exactly what the
+// one-by-one loop would have produced), (3) nodes, sub-paths and draw records are written in parallel.
+
+static void plan_fill(z2d_ctx* c, const z2d_draw_cmd& k, FillPlan& pl) {
+  memset(&pl, 0, sizeof pl);
+  const z2d_sfc* s = k.surface;
+  const z2d_fill_opts* o = k.fill;
+  const z2d_pattern* pat = k.pattern;
+  if (k.kind != 0 || !s || !pat || !o || s->ctx != c || (k.n_nodes && !k.nodes) || pat->kind != Z2D_PATTERN_OPAQUE ||
+      pat->pixel.format > Z2D_FMT_ALPHA1 || o->op >= Z2D_OP_COUNT || o->fill_rule > 1 || o->precision > 1 ||
+      o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X)
+    return;  // not eligible: the one-by-one path produces the status
+  const uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) return;  // isolated mode
+  pl.eligible = 1;
+  if (!px_can_demultiply(pat->pixel)) {
+    pl.status = Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
+    return;
+  }
+  if (k.n_nodes == 0) {
+    pl.skip = 1;
+    return;
+  }
+  if (!is_closed_node_set(k.nodes, k.n_nodes)) {
+    pl.status = Z2D_E_PATH_NOT_CLOSED;
+    return;
+  }
+  size_t first = 0;
+  while (first < k.n_nodes && k.nodes[first].tag != Z2D_NODE_MOVE_TO) {
+    if (k.nodes[first].tag == Z2D_NODE_LINE_TO || k.nodes[first].tag == Z2D_NODE_CURVE_TO) {
+      pl.status = Z2D_E_INVALID_STATE;
+      return;
+    }
+    if (k.nodes[first].tag > Z2D_NODE_CLOSE_PATH) {
+      pl.status = Z2D_E_INVALID_ARG;
+      return;
+    }
+    first++;
+  }
+  pl.first = (uint32_t)first;
+  pl.m = (uint32_t)(k.n_nodes - first);
+  pl.status = split_subpaths(k.nodes + first, pl.m, 0, 0, true, nullptr, pl.n_sp, pl.n_par);
+}
+
+static void write_fill(Batch& B, const z2d_draw_cmd& k, const FillPlan& pl) {
+  const z2d_sfc* s = k.surface;
+  const z2d_fill_opts* o = k.fill;
+  const z2d_pixel& px = k.pattern->pixel;
+  memcpy(B.nodes.p + pl.node_base, k.nodes + pl.first, (size_t)pl.m * sizeof(z2d_node));
+  uint32_t n_sp, n_par;
+  split_subpaths(k.nodes + pl.first, pl.m, pl.node_base, pl.draw_idx, true, B.subpaths.p + pl.sp_base, n_sp, n_par);
+  uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;  // as z2d_fill / record_draw
+  if (aa == Z2D_AA_DEFAULT) aa = Z2D_AA_MULTISAMPLE_4X;
+  const uint32_t precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
+  const uint32_t reduces = (o->op == Z2D_OP_SRC || (o->op == Z2D_OP_SRC_OVER && px_is_opaque(px))) ? 1u : 0u;
+  const RGBA16 v = pixel_to_rgba16(px.format, px.r, px.g, px.b, px.a);
+  DrawIn in;
+  in.surface = pl.slot;
+  in.opts = pack_draw_opts(0, aa, o->fill_rule, o->op, precision, reduces, 0);
+  in.paint_raw = pixel_to_raw(s->fmt, px.format, px.r, px.g, px.b, px.a);
+  in.px_rgba = (uint32_t)v.r | ((uint32_t)v.g << 8) | ((uint32_t)v.b << 16) | ((uint32_t)v.a << 24);
+  in.src_index = kNoIndex;
+  in.stroke_index = kNoIndex;
+  in.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;
+  B.draws.p[pl.draw_idx] = in;
+}
+
+template <class F>
+static void parallel_for(size_t n, unsigned threads, F&& fn) {  // fn(begin, end) on contiguous slices
+  if (threads <= 1 || n < 2 * threads) return fn((size_t)0, n);
+  std::vector<std::thread> pool;
+  const size_t per = (n + threads - 1) / threads;
+  for (unsigned t = 1; t < threads; t++) {
+    const size_t b = std::min(n, t * per), e = std::min(n, b + per);
+    if (b < e) pool.emplace_back([&fn, b, e] { fn(b, e); });
+  }
+  fn((size_t)0, std::min(n, per));
+  for (auto& th : pool) th.join();
+}
+
+// Records cmds[0..n) if every one of them is a plain fill; returns false (nothing recorded) otherwise.
+static bool submit_fills_parallel(z2d_ctx* c, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses, int32_t& first_err) {
+  std::vector<FillPlan>& plan = c->fill_plans;
+  plan.resize(n);
+  parallel_for(n, c->record_threads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; i++) plan_fill(c, cmds[i], plan[i]);
+  });
+  Batch& B = *c->rec;
+  size_t nodes = B.nodes.n, sps = B.subpaths.n, draws = B.draws.n;
+  uint32_t n_par = 0;
+  for (size_t i = 0; i < n; i++) {
+    FillPlan& pl = plan[i];
+    if (!pl.eligible) return false;
+    if (pl.status != Z2D_OK || pl.skip) continue;
+    pl.node_base = (uint32_t)nodes;
+    pl.sp_base = (uint32_t)sps;
+    pl.draw_idx = (uint32_t)draws;
+    nodes += pl.m;
+    sps += pl.n_sp;
+    draws += 1;
+    n_par += pl.n_par;
+  }
+  if (nodes > kMaxBatchNodes || draws > kMaxBatchDraws) return false;
+  if (!B.nodes.reserve(nodes) || !B.subpaths.reserve(sps) || !B.draws.reserve(draws)) return false;
+  for (size_t i = 0; i < n; i++)  // surface slots are batch state: serial
+    if (plan[i].status == Z2D_OK && !plan[i].skip) plan[i].slot = batch_slot(c, cmds[i].surface);
+  parallel_for(n, c->record_threads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; i++)
+      if (plan[i].status == Z2D_OK && !plan[i].skip) write_fill(B, cmds[i], plan[i]);
+  });
+  B.nodes.n = nodes;
+  B.subpaths.n = sps;
+  B.draws.n = draws;
+  B.n_par_sp += n_par;
+  for (size_t i = 0; i < n; i++) {
+    if (statuses) statuses[i] = plan[i].status;
+    if (plan[i].status != Z2D_OK && first_err == Z2D_OK) first_err = plan[i].status;
+  }
+  return true;
+}
+
+extern "C" {
+
 int32_t z2d_submit(z2d_ctx* c, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses) {
   if (!c || (n && !cmds)) return Z2D_E_INVALID_ARG;
   int32_t first = Z2D_OK;
-  for (size_t i = 0; i < n; i++) {
-    const z2d_draw_cmd& k = cmds[i];
-    int32_t rc = k.kind == 0 ? z2d_fill(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.fill)
-                             : z2d_stroke(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.stroke);
-    if (statuses) statuses[i] = rc;
-    if (rc != Z2D_OK && first == Z2D_OK) first = rc;
+  constexpr size_t kParallelMin = 2048;
+  size_t i = 0;
+  while (i < n) {
+    // a run that fits the current batch: recorded by several threads when it is long enough and all plain fills
+    const size_t room = c->chunk_draws ? (c->rec->draws.n < c->chunk_draws ? c->chunk_draws - c->rec->draws.n : 1) : n - i;
+    const size_t run = std::min(n - i, room);
+    if (run >= kParallelMin && c->record_threads > 1 && submit_fills_parallel(c, cmds + i, run, statuses ? statuses + i : nullptr, first)) {
+      i += run;
+      if (c->chunk_draws && c->rec->draws.n >= c->chunk_draws) {
+        const int rc = kick(c);  // asynchronous: the worker executes this batch while the next run is recorded
+        if (rc != Z2D_OK && first == Z2D_OK) first = rc;
+      }
+      continue;
+    }
+    const size_t end = i + (run >= kParallelMin ? run : 1);  // (a mixed run falls back to the one-by-one path)
+    for (; i < end; i++) {
+      const z2d_draw_cmd& k = cmds[i];
+      int32_t rc = k.kind == 0 ? z2d_fill(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.fill)
+                               : z2d_stroke(c, k.surface, k.pattern, k.nodes, k.n_nodes, k.stroke);
+      if (statuses) statuses[i] = rc;
+      if (rc != Z2D_OK && first == Z2D_OK) first = rc;
+    }
   }
   return first;
 }
