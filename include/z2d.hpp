@@ -19,6 +19,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <optional>
 #include <utility>
 #include <vector>
 
@@ -491,6 +492,20 @@ class Surface {
   Format getFormat() const { return (Format)z2d_surface_format(sfc_); }
   void paintPixel(const Pixel& px) { check(z2d_surface_paint_pixel(sfc_, &px.pod), dev_->handle()); }               // surface.zig:295
   void putPixel(int32_t x, int32_t y, const Pixel& px) { check(z2d_surface_put_pixel(sfc_, x, y, &px.pod), dev_->handle()); }  // surface.zig:288
+  std::optional<Pixel> getPixel(int32_t x, int32_t y) {  // surface.zig:280: nullopt outside the surface
+    Pixel px;
+    const int32_t rc = z2d_surface_get_pixel(sfc_, x, y, &px.pod);
+    if (rc == 1) return std::nullopt;
+    check(rc, dev_->handle());
+    return px;
+  }
+  // export_png.zig:150-373: the scanline bytes a PNG holds before zlib (de-multiplied, optional sRGB curve, packed greys
+  // most-significant-first), produced on the device.  flags: Z2D_EXPORT_SRGB | Z2D_EXPORT_FILTER_BYTE.
+  std::vector<uint8_t> exportRows(uint32_t flags = 0) {
+    std::vector<uint8_t> out(z2d_surface_export_size(sfc_, flags));
+    check(z2d_surface_export(sfc_, flags, out.data(), out.size()), dev_->handle());
+    return out;
+  }
   std::vector<uint8_t> download() {  // the bytes of the reference's `buf` slice (flushes and waits)
     std::vector<uint8_t> out(z2d_surface_byte_len(sfc_));
     check(z2d_surface_download(sfc_, out.data(), out.size()), dev_->handle());

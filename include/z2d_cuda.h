@@ -222,10 +222,26 @@ uint32_t z2d_surface_format(const z2d_sfc* sfc);
 int32_t z2d_surface_upload(z2d_sfc* sfc, const void* host, size_t n);
 int32_t z2d_surface_download(z2d_sfc* sfc, void* host, size_t n); /* flushes + syncs */
 void* z2d_surface_device_ptr(z2d_sfc* sfc); /* raw device pointer (interop) */
+
+/* Replaces the pixel transform of export_png.writePNGIDATStream / encodeRGBAVec (src/export_png.zig:150-373): the surface as the
+ * scanline bytes a PNG holds before zlib, produced on the device so the read-back is export-ready.  argb/rgba: R,G,B,A with the
+ * colour channels de-multiplied in integer space (src/internal/pixel_vector.zig:27-49); xrgb/rgb: R,G,B; alpha8: one grey byte;
+ * alpha4/2/1: grey samples packed most-significant-first, each row padded to a byte ((w*bits+7)/8 bytes).  Z2D_EXPORT_SRGB applies
+ * WriteToPNGFileOptions.color_profile = .srgb (round(255*pow(c/255, 1/2.2)) per colour channel; ignored for alpha formats),
+ * Z2D_EXPORT_FILTER_BYTE puts the filter-type byte 0 in front of every row.  n must equal z2d_surface_export_size().  A band
+ * surface exports the rows it holds.  Flushes + syncs like z2d_surface_download. */
+#define Z2D_EXPORT_SRGB 1u
+#define Z2D_EXPORT_FILTER_BYTE 2u
+size_t z2d_surface_export_size(const z2d_sfc* sfc, uint32_t flags);
+int32_t z2d_surface_export(z2d_sfc* sfc, uint32_t flags, void* host, size_t n);
 /* Surface.paintPixel (surface.zig:295) */
 int32_t z2d_surface_paint_pixel(z2d_sfc* sfc, const z2d_pixel* px);
 /* Surface.putPixel (surface.zig:288): out-of-bounds coordinates are ignored */
 int32_t z2d_surface_put_pixel(z2d_sfc* sfc, int32_t x, int32_t y, const z2d_pixel* px);
+/* Surface.getPixel (surface.zig:280): the pixel in the surface's own format (channel values as stored).  Returns 1 and leaves
+ * *out untouched where the reference returns null (coordinates outside the surface, or outside the rows a band holds).
+ * Flushes + syncs (a 4-byte read-back). */
+int32_t z2d_surface_get_pixel(z2d_sfc* sfc, int32_t x, int32_t y, z2d_pixel* out);
 
 /* painter.fill (painter.zig:66-143) */
 int32_t z2d_fill(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,

@@ -84,6 +84,9 @@ class Format(IntEnum):
     alpha1 = 7
 
 
+EXPORT_SRGB = 1         # z2d_surface_export flags (include/z2d_cuda.h)
+EXPORT_FILTER_BYTE = 2
+
 FORMAT_BITS = {Format.argb: 32, Format.xrgb: 32, Format.rgb: 32, Format.rgba: 32, Format.alpha8: 8, Format.alpha4: 4,
                Format.alpha2: 2, Format.alpha1: 1}
 

@@ -909,6 +909,65 @@ void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   else
     k_composite_px<<<blocks, 256, 0, st>>>(A);
 }
+// ---------------------------------------------------------------- export (export_png.zig:150-373)
+// The scanline bytes the reference hands to zlib: RGBA/ARGB de-multiplied in integer space (pixel_vector.zig:27-49) and written
+// R,G,B,A; RGB/XRGB written R,G,B; alpha8 as 8-bit grey; alpha4/2/1 re-packed MSB-first with every row starting on a byte
+// (the surface packs LSB-first with rows not byte-aligned).  With a colour profile each colour channel goes through
+// round(255 * pow(c / 255, 1 / gamma)) -- 256 possible inputs, so a table built on the host.  One item = one pixel (>= 8 bits) or
+// one output byte (packed greys).
+__global__ void __launch_bounds__(256) k_export_rows(ExportArgs A) {
+  const size_t total = (size_t)A.items_per_row * (size_t)A.h;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t y = i / A.items_per_row;
+    const uint32_t x = (uint32_t)(i - y * A.items_per_row);
+    uint8_t* row = A.out + y * A.row_bytes;
+    if (x == 0 && A.filter_byte) row[0] = 0;  // scanline header: filter type none
+    row += A.filter_byte;
+    if (A.fmt <= Z2D_FMT_RGBA) {
+      RGBA16 v = raw_to_rgba16(A.fmt, ((const uint32_t*)A.data)[y * (size_t)A.w + x]);
+      const bool alpha = A.fmt == Z2D_FMT_ARGB || A.fmt == Z2D_FMT_RGBA;
+      if (alpha) {
+        const int d = v.a > 1 ? v.a : 1;
+        v.r = v.a == 0 ? 0 : v.r * 255 / d;
+        v.g = v.a == 0 ? 0 : v.g * 255 / d;
+        v.b = v.a == 0 ? 0 : v.b * 255 / d;
+      }
+      if (A.gamma) {  // an unpremultiplied-looking pixel (c > a) can de-multiply past 255; the reference's u8 cast would trap
+        v.r = A.gamma[v.r & 255];
+        v.g = A.gamma[v.g & 255];
+        v.b = A.gamma[v.b & 255];
+      }
+      if (alpha) {
+        uint8_t* o = row + (size_t)x * 4;
+        o[0] = (uint8_t)v.r; o[1] = (uint8_t)v.g; o[2] = (uint8_t)v.b; o[3] = (uint8_t)v.a;
+      } else {
+        uint8_t* o = row + (size_t)x * 3;
+        o[0] = (uint8_t)v.r; o[1] = (uint8_t)v.g; o[2] = (uint8_t)v.b;
+      }
+    } else if (A.fmt == Z2D_FMT_ALPHA8) {
+      row[x] = A.data[y * (size_t)A.w + x];
+    } else {
+      const int bits = fmt_bits(A.fmt), per = 8 / bits;
+      uint32_t b = 0;
+      for (int k = 0; k < per; ++k) {
+        const uint32_t px = x * per + k;
+        if (px >= (uint32_t)A.w) break;
+        b |= load_raw(A.data, A.fmt, y * (size_t)A.w + px) << (8 - bits - k * bits);
+      }
+      row[x] = (uint8_t)b;
+    }
+  }
+}
+
+void launch_export(const ExportArgs& A, int sm_count, cudaStream_t st) {
+  const size_t total = (size_t)A.items_per_row * (size_t)A.h;
+  if (total == 0) return;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_export_rows<<<(unsigned)blocks, 256, 0, st>>>(A);
+}
+
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st) {
   unsigned blocks = (unsigned)((n_px + 255) / 256);
   if (blocks > 148u * 16u) blocks = 148u * 16u;

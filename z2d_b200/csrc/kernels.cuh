@@ -73,6 +73,17 @@ void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw
 void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const DevEdge* edges, uint32_t n_edges,
                              int rows, const GradTables& T, cudaStream_t st);
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st);
+struct ExportArgs {  // z2d_surface_export
+  const uint8_t* data;
+  uint32_t fmt;
+  int32_t w, h;
+  uint32_t items_per_row;  // pixels (>= 8 bits per pixel) or output bytes (packed greys)
+  uint32_t filter_byte;    // 1: every row starts with the PNG filter-type byte 0
+  size_t row_bytes;        // including the filter byte
+  const uint8_t* gamma;    // 256-entry channel table, or null (linear)
+  uint8_t* out;
+};
+void launch_export(const ExportArgs& A, int sm_count, cudaStream_t st);
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st);
 void launch_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t raw, cudaStream_t st);
 

@@ -49,8 +49,11 @@ def load_library():
         "z2d_surface_upload": (C.c_int32, [vp, vp, C.c_size_t]),
         "z2d_surface_download": (C.c_int32, [vp, vp, C.c_size_t]),
         "z2d_surface_device_ptr": (vp, [vp]),
+        "z2d_surface_export_size": (C.c_size_t, [vp, C.c_uint32]),
+        "z2d_surface_export": (C.c_int32, [vp, C.c_uint32, vp, C.c_size_t]),
         "z2d_surface_paint_pixel": (C.c_int32, [vp, P(abi.PixelPOD)]),
         "z2d_surface_put_pixel": (C.c_int32, [vp, C.c_int32, C.c_int32, P(abi.PixelPOD)]),
+        "z2d_surface_get_pixel": (C.c_int32, [vp, C.c_int32, C.c_int32, P(abi.PixelPOD)]),
         "z2d_fill": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]),
         "z2d_stroke": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.StrokeOptsPOD)]),
         "z2d_composite": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, P(abi.CompOpPOD), C.c_size_t, C.c_uint32]),
@@ -68,8 +71,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
-                    "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_paint_pixel",
-                    "z2d_surface_put_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
+                    "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel",
+                    "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
 
 
 class CudaBackend:
@@ -117,6 +120,15 @@ class CudaBackend:
         self._check(self.lib.z2d_surface_download(hd, buf.ctypes.data_as(C.c_void_p), n))
         return buf
 
+    def surface_export(self, hd, srgb=False, filter_byte=False):
+        """PNG scanline bytes (export_png.zig:150-373) produced on the device; (rows, row_bytes) uint8."""
+        flags = (abi.EXPORT_SRGB if srgb else 0) | (abi.EXPORT_FILTER_BYTE if filter_byte else 0)
+        n = self.lib.z2d_surface_export_size(hd, flags)
+        rows = self.lib.z2d_surface_height(hd)
+        buf = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.z2d_surface_export(hd, flags, buf.ctypes.data_as(C.c_void_p), n))
+        return buf.reshape(rows, n // max(1, rows))
+
     def surface_upload(self, hd, data):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         self._check(self.lib.z2d_surface_upload(hd, data.ctypes.data_as(C.c_void_p), data.size))
@@ -126,6 +138,15 @@ class CudaBackend:
 
     def surface_put_pixel(self, hd, x, y, px):
         self._check(self.lib.z2d_surface_put_pixel(hd, x, y, C.byref(px.pod())))
+
+    def surface_get_pixel(self, hd, x, y):
+        """(format, r, g, b, a) as stored, or None where Surface.getPixel returns null."""
+        pod = abi.PixelPOD()
+        rc = self.lib.z2d_surface_get_pixel(hd, x, y, C.byref(pod))
+        if rc == 1:
+            return None
+        self._check(rc)
+        return (pod.format, pod.r, pod.g, pod.b, pod.a)
 
     def surface_param(self, hd, keep):
         return hd

@@ -597,6 +597,32 @@ class Surface:
         """Reference `buf` bytes (tightly packed; sub-byte formats bit-contiguous)."""
         return self.backend.surface_download(self.handle, self.byte_len())
 
+    def export(self, profile=None, filter_byte=False):
+        """The scanline bytes export_png.writeToPNGFile compresses (export_png.zig:150-373), produced on the device:
+        (rows, row_bytes) uint8.  profile: None / "linear" / "srgb" (WriteToPNGFileOptions.color_profile)."""
+        return self.backend.surface_export(self.handle, srgb=(profile == "srgb"), filter_byte=filter_byte)
+
+    def write_png(self, filename, profile=None):
+        """export_png.writeToPNGFile (export_png.zig:36-60): magic, IHDR, optional gAMA, zlib'd scanlines, IEND.  Only the
+        pixel transform runs on the device; chunk framing and deflate stay on the host, as in the reference."""
+        import struct
+        import zlib
+
+        def chunk(tag, data):
+            return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+        fmt = Format(self.format)
+        depth = {Format.alpha4: 4, Format.alpha2: 2, Format.alpha1: 1}.get(fmt, 8)
+        color_type = 6 if fmt in (Format.argb, Format.rgba) else 2 if fmt in (Format.xrgb, Format.rgb) else 0
+        out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", self.width, self.height, depth, color_type, 0, 0, 0))
+        if profile is not None:  # export_png.zig:118-133
+            gamma = np.float32(1) / np.float32(2.2 if profile == "srgb" else 1.0)
+            out += chunk(b"gAMA", struct.pack(">I", int(np.float32(gamma * np.float32(100000)))))
+        out += chunk(b"IDAT", zlib.compress(self.export(profile, filter_byte=True).tobytes()))
+        out += chunk(b"IEND", b"")
+        with open(filename, "wb") as f:
+            f.write(out)
+
     def upload(self, data):
         data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data, dtype=np.uint8)
         assert data.size == self.byte_len()
@@ -607,6 +633,10 @@ class Surface:
 
     def put_pixel(self, x, y, px):  # surface.zig:288
         self.backend.surface_put_pixel(self.handle, int(x), int(y), px)
+
+    def get_pixel(self, x, y):  # surface.zig:280: None when (x, y) is outside the surface
+        got = self.backend.surface_get_pixel(self.handle, int(x), int(y))
+        return None if got is None else Pixel(Format(got[0]), *got[1:])
 
     def composite(self, src, operator, dst_x, dst_y, precision=Precision.integer):  # surface.zig:225-241
         SurfaceCompositor.run(self, dst_x, dst_y, [Operation(operator, src=Param.surface(src))], precision)
