@@ -182,6 +182,7 @@ Z2D_D void spline_decompose(Pt a, Pt b, Pt c, Pt d, double tol_sq, F&& line_to) 
   Knots stack[kSplineStack];
   int sp = 0;
   Knots k{a, b, c, d};
+  #pragma unroll 1
   for (;;) {
     while (!(knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2)) stack[sp++] = knots_split(k);  // k becomes the left half
     if (!pt_eq(k.a, a)) line_to(k.a);
@@ -209,6 +210,7 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
     }
   };
   const double tol_sq = tol * tol;
+  #pragma unroll 1
   for (uint32_t i = begin; i < end; i++) {
     const z2d_node nd = nodes[i];
     switch (nd.tag) {

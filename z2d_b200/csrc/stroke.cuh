@@ -56,27 +56,37 @@ Z2D_D double z_hypot(double x, double y) {
   return h;
 }
 
-Z2D_D double slope_normalize(Slope& s) {  // Slope.zig:174-214
+// The stroker's arithmetic helpers are real functions, called with values only (no pointers into the caller's frame): inlined
+// at every use they made k_flatten_count 173 000 instructions long, and its divergent threads then spent 68 % of their
+// stall samples waiting for instruction fetch (profiles/r01_stroke_flatten_ncu.json).
+struct NormSlope {
+  double dx, dy, mag;
+};
+Z2D_DN NormSlope slope_normalized(double dx, double dy) {  // Slope.zig:174-214
   double rdx, rdy, mag;
-  if (s.dx == 0.0) {
+  if (dx == 0.0) {
     rdx = 0.0;
-    if (s.dy > 0.0) { mag = s.dy; rdy = 1.0; } else { mag = -s.dy; rdy = -1.0; }
-  } else if (s.dy == 0.0) {
+    if (dy > 0.0) { mag = dy; rdy = 1.0; } else { mag = -dy; rdy = -1.0; }
+  } else if (dy == 0.0) {
     rdy = 0.0;
-    if (s.dx > 0.0) { mag = s.dx; rdx = 1.0; } else { mag = -s.dx; rdx = -1.0; }
+    if (dx > 0.0) { mag = dx; rdx = 1.0; } else { mag = -dx; rdx = -1.0; }
   } else {
-    mag = z_hypot(s.dx, s.dy);
-    rdx = s.dx / mag;
-    rdy = s.dy / mag;
+    mag = z_hypot(dx, dy);
+    rdx = dx / mag;
+    rdy = dy / mag;
   }
-  s.dx = rdx;
-  s.dy = rdy;
-  return mag;
+  return {rdx, rdy, mag};
+}
+Z2D_D double slope_normalize(Slope& s) {
+  const NormSlope r = slope_normalized(s.dx, s.dy);
+  s.dx = r.dx;
+  s.dy = r.dy;
+  return r.mag;
 }
 
 Z2D_D int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
-Z2D_D int slope_compare(Slope a, Slope b) {  // Slope.zig:46-85
+Z2D_DN int slope_compare(Slope a, Slope b) {  // Slope.zig:46-85
   const double eps = 2.220446049250313e-16;
   const double bdy = fabs(b.dy - a.dy) > eps ? b.dy : a.dy;
   const double bdx = fabs(b.dx - a.dx) > eps ? b.dx : a.dx;
@@ -160,9 +170,7 @@ Z2D_D Pt face_intersect(const Face& in, const Face& out, bool clockwise) {  // F
 }
 
 // Pen.vertexIteratorFor (Pen.zig:138-232)
-Z2D_D void pen_range(const StrokeCtx& c, Slope from, Slope to, bool clockwise, int& start_o, int& end_o) {
-  const PenV* v = c.pen;
-  const int n = c.npen;
+Z2D_DN int2 pen_range_of(const PenV* __restrict__ v, int n, Slope from, Slope to, bool clockwise) {
   int start = 0, end = 0;
   auto cw = [&](int i) Z2D_LAMBDA { return Slope{v[i].cwx, v[i].cwy}; };
   auto ccw = [&](int i) Z2D_LAMBDA { return Slope{v[i].ccwx, v[i].ccwy}; };
@@ -213,8 +221,12 @@ Z2D_D void pen_range(const StrokeCtx& c, Slope from, Slope to, bool clockwise, i
     }
     end = i;
   }
-  start_o = max(0, start);
-  end_o = max(0, end);
+  return make_int2(max(0, start), max(0, end));
+}
+Z2D_D void pen_range(const StrokeCtx& c, Slope from, Slope to, bool clockwise, int& start_o, int& end_o) {
+  const int2 r = pen_range_of(c.pen, c.npen, from, to, clockwise);
+  start_o = r.x;
+  end_o = r.y;
 }
 
 struct PointBuf25 {  // PointBuffer(2, 5) (point_buffer.zig)
@@ -245,6 +257,47 @@ struct Contour {
 struct PlotState {  // the part of the plotter the generic helpers use (Plotter and InitialPolygon)
   Contour outer, inner;
   int clockwise = -1;  // ?bool
+};
+
+// The points one line_to / curve_to node feeds to the plotter, one per call, so that a plotter has ONE line_to site for lines,
+// curves and the closing segment: a line yields its end point; a curve yields what Spline.decompose (Spline.zig:37-71) passes to
+// its callback, in the same order and computed by the same operations as spline_decompose (kernels.cu).
+struct SegIter {
+  Knots stack[kSplineStack];
+  Knots k;
+  Pt a, d;
+  double tol_sq;
+  int sp, phase;  // phase 0: subdividing, 1: end point pending, 2: done
+  Z2D_D void line(Pt p) {
+    d = p;
+    phase = 1;
+  }
+  Z2D_D void curve(Pt a_, Pt b, Pt c, Pt d_, double tsq) {
+    a = a_;
+    d = d_;
+    tol_sq = tsq;
+    sp = 0;
+    k = Knots{a_, b, c, d_};
+    phase = (pt_eq(a_, b) && pt_eq(c, d_)) ? 1 : 0;  // Spline.zig:39-42
+  }
+  Z2D_D bool next(Pt& p) {
+#pragma unroll 1
+    while (phase == 0) {
+      while (!(knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2)) stack[sp++] = knots_split(k);  // k becomes the left half
+      const Pt ka = k.a;
+      if (sp == 0) phase = 1; else k = stack[--sp];
+      if (!pt_eq(ka, a)) {
+        p = ka;
+        return true;
+      }
+    }
+    if (phase == 1) {
+      p = d;
+      phase = 2;
+      return true;
+    }
+    return false;
+  }
 };
 
 template <class Sink>
@@ -304,46 +357,59 @@ struct Stroker {
     ct.len = 0;
   }
 
-  // ---- caps (Face.zig:154-284); `emit(p)` receives the cap points in order
+  // ---- caps (Face.zig:154-284); `emit(p)` receives the cap points in order.  Written as one loop over "fixed head points, pen
+  // vertices, fixed tail point" so that `emit` (which ends in the edge sink) is instantiated once per cap, not once per point.
   template <class F>
   Z2D_D void cap(const Face& f, bool clockwise, F&& emit) {
+    Pt h0, h1, h2{}, h3{};
+    int n_head, idx = 0, end = 0;
+    bool tail = false;
     switch (c.cap) {
       case Z2D_CAP_BUTT:
-        if (clockwise) { emit(f.p1_ccw); emit(f.p1_cw); } else { emit(f.p1_cw); emit(f.p1_ccw); }
+        n_head = 2;
+        h0 = clockwise ? f.p1_ccw : f.p1_cw;
+        h1 = clockwise ? f.p1_cw : f.p1_ccw;
         break;
       case Z2D_CAP_SQUARE: {
         double ox = f.user.dx * f.half_width, oy = f.user.dy * f.half_width;
         xf_dist(c.ctm, ox, oy);
-        if (clockwise) {
-          emit(f.p1_ccw);
-          emit({f.p1_ccw.x + ox, f.p1_ccw.y + oy});
-          emit({f.p1_cw.x + ox, f.p1_cw.y + oy});
-          emit(f.p1_cw);
-        } else {
-          emit(f.p1_cw);
-          emit({f.p1_cw.x + ox, f.p1_cw.y + oy});
-          emit({f.p1_ccw.x + ox, f.p1_ccw.y + oy});
-          emit(f.p1_ccw);
-        }
+        n_head = 4;
+        h0 = clockwise ? f.p1_ccw : f.p1_cw;
+        h3 = clockwise ? f.p1_cw : f.p1_ccw;
+        h1 = {h0.x + ox, h0.y + oy};
+        h2 = {h3.x + ox, h3.y + oy};
         break;
       }
-      default: {
-        emit(clockwise ? f.p1_ccw : f.p1_cw);
-        int idx, end;
+      default:
+        n_head = 1;
+        h0 = clockwise ? f.p1_ccw : f.p1_cw;
+        h1 = clockwise ? f.p1_cw : f.p1_ccw;  // the tail point
+        tail = true;
         pen_range(c, f.dev, Slope{-f.dev.dx, -f.dev.dy}, clockwise, idx, end);
-        while (idx != end) {  // VertexIterator.next
-          const PenV v = c.pen[idx];
-          if (clockwise) {
-            idx += 1;
-            if (idx == c.npen) idx = 0;
-          } else {
-            if (idx == 0) idx = c.npen;
-            idx -= 1;
-          }
-          emit({f.p1.x + v.px, f.p1.y + v.py});
+    }
+    #pragma unroll 1
+    for (int k = 0;;) {
+      Pt p;
+      if (k < n_head) {
+        p = k == 0 ? h0 : k == 1 ? h1 : k == 2 ? h2 : h3;
+        k++;
+      } else if (idx != end) {  // VertexIterator.next
+        const PenV v = c.pen[idx];
+        if (clockwise) {
+          idx += 1;
+          if (idx == c.npen) idx = 0;
+        } else {
+          if (idx == 0) idx = c.npen;
+          idx -= 1;
         }
-        emit(clockwise ? f.p1_cw : f.p1_ccw);
+        p = {f.p1.x + v.px, f.p1.y + v.py};
+      } else if (tail) {
+        p = h1;
+        tail = false;
+      } else {
+        break;
       }
+      emit(p);
     }
   }
 
@@ -361,42 +427,84 @@ struct Stroker {
     const bool switched = join_cw != poly_cw;
     Block blk;
     blk.active = use_before && st.outer.len > 0;
-    auto plot_outer = [&](Pt p) Z2D_LAMBDA {
-      if (blk.active) block_push(st.outer, blk, p); else append(st.outer, p);
-    };
-    auto plot_inner = [&](Pt p) Z2D_LAMBDA { prepend(st.inner, p); };
-    auto outer_j = [&](Pt p) Z2D_LAMBDA { if (switched) plot_inner(p); else plot_outer(p); };
-    auto inner_j = [&](Pt p) Z2D_LAMBDA { if (switched) plot_outer(p); else plot_inner(p); };
-
+    // The join's points in emission order: outer side = o0, pen vertices [idx, end), o1; inner side = i0, p1, i1 (only i0 when
+    // the faces are parallel).  One loop with one plotting site, so the edge sink is instantiated once per join.
+    Pt o0, o1{};
+    int n_o0 = 1, idx = 0, end = 0;
+    bool has_o1 = false;
+    int n_inner = 3;
     if (cmp == 0) {
-      outer_j(join_cw ? in.p1_ccw : in.p1_cw);
-      inner_j(join_cw ? in.p1_cw : in.p1_ccw);
+      o0 = join_cw ? in.p1_ccw : in.p1_cw;
+      n_inner = 1;
+    } else if (join_mode == Z2D_JOIN_ROUND) {
+      o0 = join_cw ? in.p1_ccw : in.p1_cw;
+      pen_range(c, in.dev, out.dev, join_cw, idx, end);
+      o1 = join_cw ? out.p0_ccw : out.p0_cw;
+      has_o1 = true;
+    } else if (join_mode == Z2D_JOIN_MITER && miter_within_limit(in.dev, out.dev, c.miter_limit)) {
+      o0 = face_intersect(in, out, join_cw);
     } else {
-      if (join_mode == Z2D_JOIN_ROUND) {
-        outer_j(join_cw ? in.p1_ccw : in.p1_cw);
-        int idx, end;
-        pen_range(c, in.dev, out.dev, join_cw, idx, end);
-        while (idx != end) {
-          const PenV v = c.pen[idx];
-          if (join_cw) {
-            idx += 1;
-            if (idx == c.npen) idx = 0;
-          } else {
-            if (idx == 0) idx = c.npen;
-            idx -= 1;
-          }
-          outer_j({p1.x + v.px, p1.y + v.py});
+      o0 = join_cw ? in.p1_ccw : in.p1_cw;
+      o1 = join_cw ? out.p0_ccw : out.p0_cw;
+      has_o1 = true;
+    }
+    const Pt i0 = join_cw ? in.p1_cw : in.p1_ccw, i1 = join_cw ? out.p0_cw : out.p0_ccw;
+    #pragma unroll 1
+    for (int ki = 0;;) {
+      Pt p;
+      bool outer_side = true;
+      if (n_o0) {
+        p = o0;
+        n_o0 = 0;
+      } else if (idx != end) {
+        const PenV v = c.pen[idx];
+        if (join_cw) {
+          idx += 1;
+          if (idx == c.npen) idx = 0;
+        } else {
+          if (idx == 0) idx = c.npen;
+          idx -= 1;
         }
-        outer_j(join_cw ? out.p0_ccw : out.p0_cw);
-      } else if (join_mode == Z2D_JOIN_MITER && miter_within_limit(in.dev, out.dev, c.miter_limit)) {
-        outer_j(face_intersect(in, out, join_cw));
+        p = {p1.x + v.px, p1.y + v.py};
+      } else if (has_o1) {
+        p = o1;
+        has_o1 = false;
+      } else if (ki < n_inner) {
+        p = ki == 0 ? i0 : ki == 1 ? p1 : i1;
+        outer_side = false;
+        ki++;
       } else {
-        outer_j(join_cw ? in.p1_ccw : in.p1_cw);
-        outer_j(join_cw ? out.p0_ccw : out.p0_cw);
+        break;
       }
-      inner_j(join_cw ? in.p1_cw : in.p1_ccw);
-      inner_j(p1);
-      inner_j(join_cw ? out.p0_cw : out.p0_ccw);
+      // outer-side points go to the outer contour (appended, or inserted before its first node) unless the join turns against
+      // the polygon's direction, in which case the sides swap; inner-side points are prepended to the inner contour
+      const Pt sp = scaled(p);
+      Pt a, b;
+      bool have;
+      if (outer_side == switched) {  // prepend(st.inner, p)
+        have = st.inner.len != 0;
+        a = sp;
+        b = st.inner.first;
+        if (!have) st.inner.last = sp;
+        st.inner.first = sp;
+        st.inner.len++;
+      } else if (blk.active) {  // block_push(st.outer, blk, p)
+        have = blk.any;
+        a = blk.prev;
+        b = sp;
+        if (!have) blk.first = sp;
+        blk.prev = sp;
+        blk.any = true;
+        st.outer.len++;
+      } else {  // append(st.outer, p)
+        have = st.outer.len != 0;
+        a = st.outer.last;
+        b = sp;
+        if (!have) st.outer.first = sp;
+        st.outer.last = sp;
+        st.outer.len++;
+      }
+      if (have) sink.add(a, b);
     }
     if (blk.active) block_end(st.outer, blk);
     if (st.clockwise < 0) st.clockwise = poly_cw ? 1 : 0;
@@ -443,6 +551,7 @@ struct Stroker {
   }
 
   Z2D_D void pen_circle(PlotState& st, Pt point) {
+    #pragma unroll 1
     for (int i = 0; i < c.npen; i++) append(st.outer, {point.x + c.pen[i].px, point.y + c.pen[i].py});
     close_contour(st.outer);
   }
@@ -466,34 +575,43 @@ struct Stroker {
       if (pts.len == 2) plot_single(st, pts.head(0), pts.head(1));
       else if (pts.len > 2) plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
     };
-    for (uint32_t i = begin; i < end; i++) {
-      const z2d_node nd = nodes[i];
-      switch (nd.tag) {
-        case Z2D_NODE_MOVE_TO:
-          if (pts.len > 0) finish();
-          pts.reset();
-          pts.add({nd.p[0], nd.p[1]});
-          break;
-        case Z2D_NODE_LINE_TO: line_to(c.join, {nd.p[0], nd.p[1]}); break;
-        case Z2D_NODE_CURVE_TO:
-          if (pts.len == 0) break;
-          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) Z2D_LAMBDA { line_to(Z2D_JOIN_ROUND, p); });
-          break;
-        default:  // close_path (stroke_plotter.zig:157-180)
-          if (pts.len == 1) {
-            if (c.cap == Z2D_CAP_ROUND) {  // plotDotted (202-237)
-              pen_circle(st, pts.first());
-              st.clockwise = -1;
-            }
-          } else if (pts.len == 2) {
-            plot_single(st, pts.head(0), pts.head(1));
-          } else if (pts.len > 2) {
-            plot_closed_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
+    SegIter it;
+#pragma unroll 1
+    for (uint32_t i = begin; i <= end; i++) {  // one extra trip: the end of the node list finishes like a move_to
+      const bool at_end = i == end;
+      const z2d_node nd = nodes[at_end ? begin : i];
+      const uint32_t tag = at_end ? (uint32_t)Z2D_NODE_MOVE_TO : nd.tag;
+      if (tag == Z2D_NODE_MOVE_TO) {
+        finish();
+        if (at_end) break;
+        pts.reset();
+        pts.add({nd.p[0], nd.p[1]});
+      } else if (tag == Z2D_NODE_LINE_TO || tag == Z2D_NODE_CURVE_TO) {
+        if (pts.len == 0) continue;
+        uint32_t jm = c.join;
+        if (tag == Z2D_NODE_LINE_TO) {
+          it.line({nd.p[0], nd.p[1]});
+        } else {
+          it.curve(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, c.tolerance * c.tolerance);
+          jm = Z2D_JOIN_ROUND;
+        }
+        Pt p;
+#pragma unroll 1
+        while (it.next(p)) line_to(jm, p);
+      } else {  // close_path (stroke_plotter.zig:157-180)
+        if (pts.len == 1) {
+          if (c.cap == Z2D_CAP_ROUND) {  // plotDotted (202-237)
+            pen_circle(st, pts.first());
+            st.clockwise = -1;
           }
-          pts.reset();
+        } else if (pts.len == 2) {
+          plot_single(st, pts.head(0), pts.head(1));
+        } else if (pts.len > 2) {
+          plot_closed_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
+        }
+        pts.reset();
       }
     }
-    finish();
   }
 
   // =============================== dashed (dashed_plotter.zig)
@@ -604,6 +722,7 @@ struct Stroker {
       const double total_len = slope_normalize(slope);
       double remaining = total_len;
       double step_len = fmin(dasher.remain, remaining);
+      #pragma unroll 1
       while (remaining > 0) {
         remaining -= step_len;
         double xo = slope.dx * (total_len - remaining), yo = slope.dy * (total_len - remaining);
@@ -640,54 +759,62 @@ struct Stroker {
       st.clockwise = -1;
     };
 
-    for (uint32_t i = begin; i < end; i++) {
-      const z2d_node nd = nodes[i];
-      switch (nd.tag) {
-        case Z2D_NODE_MOVE_TO:
-          finish();
-          dasher.reset();
-          pts.reset();
-          pts.add({nd.p[0], nd.p[1]});
-          break;
-        case Z2D_NODE_LINE_TO: line_to(c.join, {nd.p[0], nd.p[1]}); break;
-        case Z2D_NODE_CURVE_TO:
-          if (pts.len == 0) break;
-          spline(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, [&](Pt p) Z2D_LAMBDA { line_to(Z2D_JOIN_ROUND, p); });
-          break;
-        default: {  // close_path (202-305)
-          if (pts.len == 0) break;
-          const Pt target = initial_kind == 2 ? ipts.first() : (initial_kind == 1 ? initial_off : pts.first());
-          line_to(c.join, target);
-          if (initial_kind == 2) {
-            if (dasher.on && pts.len > 1) {
-              if (ipts.len == 1) {
-                plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
-                initial_kind = 0;
-              } else {
-                join_and_cap_initial();
-              }
+    SegIter it;
+#pragma unroll 1
+    for (uint32_t i = begin; i <= end; i++) {  // one extra trip: the end of the node list finishes like a move_to
+      const bool at_end = i == end;
+      const z2d_node nd = nodes[at_end ? begin : i];
+      const uint32_t tag = at_end ? (uint32_t)Z2D_NODE_MOVE_TO : nd.tag;
+      if (tag == Z2D_NODE_MOVE_TO) {
+        finish();
+        if (at_end) break;
+        dasher.reset();
+        pts.reset();
+        pts.add({nd.p[0], nd.p[1]});
+        continue;
+      }
+      if (pts.len == 0) continue;  // line_to / curve_to / close_path without a current point
+      uint32_t jm = c.join;
+      if (tag == Z2D_NODE_LINE_TO) {
+        it.line({nd.p[0], nd.p[1]});
+      } else if (tag == Z2D_NODE_CURVE_TO) {
+        it.curve(pts.last(), {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, c.tolerance * c.tolerance);
+        jm = Z2D_JOIN_ROUND;
+      } else {  // close_path (202-305): first a line to where the sub-path began
+        it.line(initial_kind == 2 ? ipts.first() : (initial_kind == 1 ? initial_off : pts.first()));
+      }
+      Pt p;
+#pragma unroll 1
+      while (it.next(p)) line_to(jm, p);
+      if (tag != Z2D_NODE_LINE_TO && tag != Z2D_NODE_CURVE_TO) {
+        if (initial_kind == 2) {
+          if (dasher.on && pts.len > 1) {
+            if (ipts.len == 1) {
+              plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
+              initial_kind = 0;
             } else {
-              finish_initial();
+              join_and_cap_initial();
             }
-          } else if (initial_kind == 1) {
-            initial_kind = 0;
           } else {
-            if (pts.len == 1) {
-              plot_dotted_dashed(st, pts.first(), cur_slope);
-            } else if (pts.len == 2) {
-              plot_single(st, pts.head(0), pts.head(1));
-            } else {
-              join(st, c.join, pts.tail(2), pts.head(0), pts.head(1), false);
-              close_contour(st.outer);
-              close_contour(st.inner);
-              st.clockwise = -1;
-            }
+            finish_initial();
           }
-          pts.reset();
+        } else if (initial_kind == 1) {
+          initial_kind = 0;
+        } else {
+          if (pts.len == 1) {
+            plot_dotted_dashed(st, pts.first(), cur_slope);
+          } else if (pts.len == 2) {
+            plot_single(st, pts.head(0), pts.head(1));
+          } else {
+            join(st, c.join, pts.tail(2), pts.head(0), pts.head(1), false);
+            close_contour(st.outer);
+            close_contour(st.inner);
+            st.clockwise = -1;
+          }
         }
+        pts.reset();
       }
     }
-    finish();
   }
 };
 

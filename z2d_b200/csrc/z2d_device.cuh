@@ -19,6 +19,7 @@
 
 #define Z2D_HD __host__ __device__ __forceinline__
 #define Z2D_D __device__ __forceinline__
+#define Z2D_DN __device__ __noinline__  // only for functions whose arguments and results are values (see Z2D_LAMBDA)
 // Local lambdas must be inlined too: ptxas otherwise emits them as called sub-functions of the kernel that receive GENERIC
 // pointers into the caller's stack frame, and with the large flatten kernels such a call was observed to be passed a frame
 // address built from a clobbered uniform register (an illegal read in k_flatten_count depending on the build).
