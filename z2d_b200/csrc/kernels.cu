@@ -244,9 +244,10 @@ namespace z2d {
 
 __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
                                 DevDraw* __restrict__ draws, uint32_t* __restrict__ sp_count, const PenV* __restrict__ pens,
-                                const double* __restrict__ dashes) {
+                                const double* __restrict__ dashes, const uint32_t* __restrict__ order) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
+  if (order) i = order[i];
   const DevSubPath sp = sps[i];
   if (sp.flags & kSpNodeParallel) {
     sp_count[i] = 0;
@@ -271,9 +272,10 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
 __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
                                const DevDraw* __restrict__ draws, const uint32_t* __restrict__ sp_off,
                                DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw, const PenV* __restrict__ pens,
-                               const double* __restrict__ dashes) {
+                               const double* __restrict__ dashes, const uint32_t* __restrict__ order) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sp) return;
+  if (order) i = order[i];
   const DevSubPath sp = sps[i];
   if (sp.flags & kSpNodeParallel) return;
   const DevDraw& d = draws[sp.draw];
@@ -284,6 +286,52 @@ __global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp
   sink.draw = sp.draw;
   if (d.kind == 0) fill_subpath<true>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
   else stroke_subpath<true>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
+}
+
+// ---- thread -> sub-path order for the sequential plotters.  A warp whose 32 lanes walk 32 differently styled strokes runs
+// with 2.4 active lanes (ncu, profiles/r01_stroke_flatten_ncu.json); lanes that plot the same kind of stroke follow the same
+// branches.  Sub-paths are bucketed by (dashed, join, cap, pen size class, node count) with a counting sort; the heaviest
+// buckets (dashed, many nodes) come first so they do not form the tail of the launch.  Only the thread mapping changes: every
+// sub-path still writes its own count slot and its own edge range.
+constexpr int kSpKeys = 1024;
+Z2D_D uint32_t sp_key(const DevSubPath& sp, const DevDraw* __restrict__ draws) {
+  if (sp.flags & kSpNodeParallel) return 0;  // returns at once in the sequential kernels: keep them together at the end
+  const DevDraw& d = draws[sp.draw];
+  const uint32_t nn = min(sp.node_end - sp.node_begin, 15u);
+  if (d.kind == 0) return 1 + nn;  // irregular fills
+  const uint32_t lg = 31u - (uint32_t)__clz(d.pen_count | 1u);           // pen vertices: 4-7, 8-15, 16-31, 32+
+  const uint32_t pen = lg < 2u ? 0u : min(lg - 2u, 3u);
+  return ((d.dash_count ? 1u : 0u) << 9) | (nn << 5) | (pen << 3) | ((d.join == Z2D_JOIN_ROUND ? 1u : 0u) << 2) | min(d.cap, 3u);
+}
+__global__ void k_sp_hist(const DevSubPath* __restrict__ sps, uint32_t n_sp, const DevDraw* __restrict__ draws, uint32_t* __restrict__ hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_sp) atomicAdd(&hist[sp_key(sps[i], draws)], 1u);
+}
+__global__ void __launch_bounds__(kSpKeys) k_sp_cursor(uint32_t* __restrict__ hist) {  // descending exclusive scan, in place
+  __shared__ uint32_t s[kSpKeys];
+  const int t = threadIdx.x;
+  const uint32_t mine = hist[kSpKeys - 1 - t];  // t = 0 is the largest key
+  s[t] = mine;
+  __syncthreads();
+  for (int off = 1; off < kSpKeys; off <<= 1) {
+    const uint32_t v = t >= off ? s[t - off] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  hist[kSpKeys - 1 - t] = s[t] - mine;
+}
+__global__ void k_sp_scatter(const DevSubPath* __restrict__ sps, uint32_t n_sp, const DevDraw* __restrict__ draws, uint32_t* __restrict__ cursor,
+                             uint32_t* __restrict__ order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_sp) order[atomicAdd(&cursor[sp_key(sps[i], draws)], 1u)] = i;
+}
+void launch_sp_order(const DevSubPath* sps, uint32_t n_sp, const DevDraw* draws, uint32_t* keys_scratch, uint32_t* order, cudaStream_t st) {
+  if (!n_sp) return;
+  cudaMemsetAsync(keys_scratch, 0, kSpKeys * 4, st);
+  k_sp_hist<<<(n_sp + 255) / 256, 256, 0, st>>>(sps, n_sp, draws, keys_scratch);
+  k_sp_cursor<<<1, kSpKeys, 0, st>>>(keys_scratch);
+  k_sp_scatter<<<(n_sp + 255) / 256, 256, 0, st>>>(sps, n_sp, draws, keys_scratch, order);
 }
 
 // ---- node-parallel flattening of simple fill sub-paths (move_to, segments..., close_path; the host guarantees at least two
@@ -825,12 +873,12 @@ void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint3
 }
 
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
-                          const double* dashes, cudaStream_t st) {
-  if (n_sp) k_flatten_count<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes);
+                          const double* dashes, const uint32_t* order, cudaStream_t st) {
+  if (n_sp) k_flatten_count<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes, order);
 }
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
-                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st) {
-  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes);
+                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st) {
+  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes, order);
 }
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
                           DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,

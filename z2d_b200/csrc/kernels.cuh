@@ -50,9 +50,12 @@ void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp
 
 // pens: array of 6-double pen vertices {px,py,cw.dx,cw.dy,ccw.dx,ccw.dy} (tess/Pen.zig), dashes: concatenated dash arrays
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
-                          const double* dashes, cudaStream_t st);
+                          const double* dashes, const uint32_t* order, cudaStream_t st);
+// order[t] = the sub-path thread t of the two kernels above plots (sub-paths bucketed by stroke style; null = identity);
+// keys_scratch: 1024 uint32
+void launch_sp_order(const DevSubPath* sps, uint32_t n_sp, const DevDraw* draws, uint32_t* keys_scratch, uint32_t* order, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
-                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, cudaStream_t st);
+                         DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st);
 // node-parallel flattening of the sub-paths flagged kSpNodeParallel: count pass (emit = false: also builds node_sp) / emit pass
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
                           DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,

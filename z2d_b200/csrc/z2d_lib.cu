@@ -91,7 +91,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0;
   int set = 0;  // which InputSet holds the batch
   size_t n_nodes = 0, h2d_bytes = 0;
 };
@@ -173,7 +173,7 @@ struct z2d_ctx {
   InputSet in[2];
   cudaStream_t copy_stream = nullptr;  // H2D of batch inputs
   cudaEvent_t ev_up = nullptr;
-  DevBuf d_node_sp, d_curve_list;
+  DevBuf d_node_sp, d_curve_list, d_sp_order, d_sp_keys;
   DevBuf d_blue, d_draws;
   DevBuf d_sp_count, d_sp_off, d_edges, d_edge_draw, d_draw_bands, d_draw_band_off, d_band_count, d_band_off, d_band_cursor;
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
@@ -521,8 +521,17 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   const bool par = m.n_par_sp != 0;
   const uint32_t n_cnt = n_sp + (par ? n_nodes : 0u);
   CK(c, c->d_sp_count.ensure((size_t)n_cnt * 4 + 16));
+  // batches with strokes: threads take sub-paths in style order so that the lanes of a warp follow the same branches
+  const uint32_t* order = nullptr;
+  if (m.n_strokes >= 64) {
+    CK(c, c->d_sp_order.ensure((size_t)n_sp * 4 + 16));
+    CK(c, c->d_sp_keys.ensure(1024 * 4));
+    launch_sp_order(S.d_subpaths.as<DevSubPath>(), n_sp, c->d_draws.as<DevDraw>(), c->d_sp_keys.as<uint32_t>(), c->d_sp_order.as<uint32_t>(), st);
+    order = c->d_sp_order.as<uint32_t>();
+    launches += 3;
+  }
   launch_flatten_count(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
-                       S.pens, S.dashes, st);
+                       S.pens, S.dashes, order, st);
   if (par) {
     CK(c, c->d_node_sp.ensure((size_t)n_nodes * 4 + 16));
     CK(c, c->d_curve_list.ensure(((size_t)n_nodes + 1) * 4 + 16));
@@ -559,7 +568,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
   CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
   launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, st);
+                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, order, st);
   if (par) {
     launch_flatten_nodes(true, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
                          c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
@@ -642,7 +651,7 @@ int run_isolated(z2d_ctx* c, Batch& B) {
     const uint32_t n_sp = m.n_sp;
     CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
     launch_flatten_count(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
-                         S.pens, S.dashes, st);
+                         S.pens, S.dashes, nullptr, st);
     CK(c, c->d_sp_off.ensure(((size_t)n_sp + 1) * 4));
     CK(c, c->d_scan_tmp.ensure(scan_tmp_len(n_sp) * 4));
     exclusive_scan(c->d_sp_count.as<uint32_t>(), c->d_sp_off.as<uint32_t>(), n_sp, c->d_scan_tmp.as<uint32_t>(), st);
@@ -651,7 +660,7 @@ int run_isolated(z2d_ctx* c, Batch& B) {
     CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
     CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
     launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, st);
+                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, nullptr, st);
     launch_direct_unbounded(S.sfcs, c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, B.batch_sfcs[0]->h, T, st);
     launches = 7;
   }
@@ -781,6 +790,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.n_draws = n_draws;
   m.n_sp = n_sp;
   m.n_par_sp = B.n_par_sp;
+  m.n_strokes = (uint32_t)B.strokes.size();
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
   m.n_work = n_work;
@@ -1015,7 +1025,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   cudaStreamSynchronize(c->stream);
   clear_batch(c, c->bat[0]);
   clear_batch(c, c->bat[1]);
-  DevBuf* bufs[] = {&c->d_blue, &c->d_draws, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands,
+  DevBuf* bufs[] = {&c->d_blue, &c->d_draws, &c->d_sp_order, &c->d_sp_keys, &c->d_sp_count, &c->d_sp_off, &c->d_edges, &c->d_edge_draw, &c->d_draw_bands,
                     &c->d_draw_band_off, &c->d_band_count, &c->d_band_off, &c->d_band_cursor, &c->d_band_edges, &c->d_list_cnt,
                     &c->d_list_off, &c->d_list_items, &c->d_scan_tmp, &c->d_comp_grads, &c->d_comp_stop_off, &c->d_comp_stop_col,
                     &c->d_node_sp, &c->d_curve_list};
