@@ -242,7 +242,13 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
 #include "stroke.cuh"
 namespace z2d {
 
-__global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
+#ifndef Z2D_FLATTEN_THREADS
+#define Z2D_FLATTEN_THREADS 64
+#endif
+#ifndef Z2D_FLATTEN_MIN_CTAS
+#define Z2D_FLATTEN_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
                                 DevDraw* __restrict__ draws, uint32_t* __restrict__ sp_count, const PenV* __restrict__ pens,
                                 const double* __restrict__ dashes, const uint32_t* __restrict__ order) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,7 +275,7 @@ __global__ void k_flatten_count(const DevSubPath* __restrict__ sps, uint32_t n_s
   }
 }
 
-__global__ void k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
+__global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_flatten_emit(const DevSubPath* __restrict__ sps, uint32_t n_sp, const z2d_node* __restrict__ nodes,
                                const DevDraw* __restrict__ draws, const uint32_t* __restrict__ sp_off,
                                DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw, const PenV* __restrict__ pens,
                                const double* __restrict__ dashes, const uint32_t* __restrict__ order) {
@@ -874,11 +880,11 @@ void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint3
 
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
                           const double* dashes, const uint32_t* order, cudaStream_t st) {
-  if (n_sp) k_flatten_count<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes, order);
+  if (n_sp) k_flatten_count<<<blocks_for(n_sp, Z2D_FLATTEN_THREADS), Z2D_FLATTEN_THREADS, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes, order);
 }
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st) {
-  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes, order);
+  if (n_sp) k_flatten_emit<<<blocks_for(n_sp, Z2D_FLATTEN_THREADS), Z2D_FLATTEN_THREADS, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes, order);
 }
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
                           DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,
