@@ -135,10 +135,26 @@ struct EdgeSink {
   bool unpaired = false;
   double scale;
   uint32_t n = 0;
-  double top, bottom, left, right;
+  double top = 0, bottom = 0, left = 0, right = 0;
   DevEdge* out = nullptr;
   uint32_t* out_draw = nullptr;
   uint32_t draw = 0;
+  uint32_t limit = 0xffffffffu;  // emit pass: number of edges the count pass found for this sink
+  // The plotters emit a contour's edges as its points arrive.  Where the reference throws an unfinished contour away (its points
+  // were only buffered), the edges emitted since a mark are taken back: count and extents in the count pass, the write position
+  // in the emit pass.
+  struct Mark {
+    uint32_t n;
+    double top, bottom, left, right;
+  };
+  Z2D_D Mark mark() const { return Mark{n, top, bottom, left, right}; }
+  Z2D_D void rewind(const Mark& m) {
+    n = m.n;
+    top = m.top;
+    bottom = m.bottom;
+    left = m.left;
+    right = m.right;
+  }
   Z2D_D void add(Pt p0, Pt p1) {
     double ax = p0.x * scale, ay = p0.y * scale, bx = p1.x * scale, by = p1.y * scale;
     DevEdge e;
@@ -150,8 +166,12 @@ struct EdgeSink {
       return;
     }
     if (EMIT) {
-      out[n] = e;
-      out_draw[n] = draw;
+      // positions at or beyond the count pass's total are always taken back by a later rewind(): never touch the slots of the
+      // next sub-path, which another thread is writing
+      if (n < limit) {
+        out[n] = e;
+        out_draw[n] = draw;
+      }
     } else {
       double t = ay < by ? ay : by, b = ay < by ? by : ay;
       double l = ax < bx ? ax : bx, r = ax < bx ? bx : ax;
@@ -290,6 +310,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
   sink.out = edges + sp_off[i];
   sink.out_draw = edge_draw + sp_off[i];
   sink.draw = sp.draw;
+  sink.limit = sp_off[i + 1] - sp_off[i];
   if (d.kind == 0) fill_subpath<true>(nodes, sp.node_begin, sp.node_end, d.tolerance, sink);
   else stroke_subpath<true>(nodes, sp.node_begin, sp.node_end, d, pens, dashes, sink);
 }

@@ -696,11 +696,13 @@ struct Stroker {
       st.inner.len = 0;
       st.clockwise = -1;
     };
+    auto seg_mark = sink.mark();  // sink position where the dash in progress began
     auto next_segment = [&](Pt point) Z2D_LAMBDA {  // 307-332
       if (initial_kind == 0) save_initial();
       else if (!dasher.on) emit_current();
       pts.reset();
       pts.add(point);
+      seg_mark = sink.mark();
     };
     auto finish_initial = [&]() Z2D_LAMBDA {  // finishInitialDotted / finishInitial (522-552)
       if (ipts.len == 1) {
@@ -771,6 +773,7 @@ struct Stroker {
         dasher.reset();
         pts.reset();
         pts.add({nd.p[0], nd.p[1]});
+        seg_mark = sink.mark();
         continue;
       }
       if (pts.len == 0) continue;  // line_to / curve_to / close_path without a current point
@@ -799,7 +802,13 @@ struct Stroker {
             finish_initial();
           }
         } else if (initial_kind == 1) {
+          // "we've already drawn back to the initial point" (dashed_plotter.zig:258-262): the reference resets the point buffer
+          // here, so a dash still in progress is never capped and its buffered join points never become edges
           initial_kind = 0;
+          sink.rewind(seg_mark);
+          st.outer.len = 0;
+          st.inner.len = 0;
+          st.clockwise = -1;
         } else {
           if (pts.len == 1) {
             plot_dotted_dashed(st, pts.first(), cur_slope);

@@ -892,8 +892,14 @@ bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23
 // count only.  Flags sub-paths eligible for node-parallel flattening (kSpNodeParallel): move_to, segments..., one close_path
 // at the very end, and at least two segments whose end differs from their start (then the plotter holds >= 3 points at the
 // close, fill_plotter.zig:82).
+//
+// keep_lone (dashed strokes with round or square caps): a sub-path without a single segment that moves -- a lone move_to, or
+// move_to + close_path -- is not dropped.  The dashed plotter finishes it as a dot when the dash pattern starts "on"
+// (dashed_plotter.zig:334-367 and 266-271, plotDotted 369-465), and a square dot is oriented by the slope the plotter last saw
+// -- state that survives move_to (current_slope, dashed_plotter.zig:98).  Such a sub-path is appended to the sub-path before it
+// (one thread plots both, in order) or, at the start of the list, becomes a sub-path of its own.
 int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_index, bool allow_parallel, DevSubPath* out, uint32_t& n_sp,
-                   uint32_t& n_par) {
+                   uint32_t& n_par, bool keep_lone = false) {
   n_sp = 0;
   n_par = 0;
   size_t i = 0;
@@ -902,21 +908,36 @@ int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_ind
     double cx = q[i].p[0], cy = q[i].p[1];
     int moving = 0;
     bool simple = allow_parallel;
+    bool any_seg = false, slope_dep = false;  // slope_dep: reaches a dot (close / end) before any segment set the plotter's slope
     while (j < m && q[j].tag != Z2D_NODE_MOVE_TO) {
       const uint32_t tag = q[j].tag;
       if (tag > Z2D_NODE_CLOSE_PATH) return Z2D_E_INVALID_ARG;
       if (tag == Z2D_NODE_CLOSE_PATH) {
         if (j + 1 < m && q[j + 1].tag != Z2D_NODE_MOVE_TO) simple = false;  // something follows the close
+        if (!any_seg) slope_dep = true;
       } else {
         const double ex = tag == Z2D_NODE_CURVE_TO ? q[j].p[4] : q[j].p[0], ey = tag == Z2D_NODE_CURVE_TO ? q[j].p[5] : q[j].p[1];
         moving += (ex != cx || ey != cy);
+        any_seg = any_seg || ex != cx || ey != cy ||
+                  (tag == Z2D_NODE_CURVE_TO && (q[j].p[0] != cx || q[j].p[1] != cy || q[j].p[2] != cx || q[j].p[3] != cy));
         cx = ex;
         cy = ey;
       }
       j++;
     }
+    if (!any_seg) slope_dep = true;
     simple = simple && q[j - 1].tag == Z2D_NODE_CLOSE_PATH && moving >= 2;
-    if (j - i > 1) {
+    if (keep_lone && slope_dep) {
+      if (n_sp > 0) {  // sub-paths of one draw are contiguous: extend the previous one over this sub-path
+        if (out) {
+          out[n_sp - 1].node_end = base + (uint32_t)j;
+          out[n_sp - 1].flags = (out[n_sp - 1].flags & ~kSpLastOfDraw) | ((j == m) ? kSpLastOfDraw : 0u);
+        }
+      } else {
+        if (out) out[n_sp] = DevSubPath{draw_index, base + (uint32_t)i, base + (uint32_t)j, (j == m) ? kSpLastOfDraw : 0u};
+        n_sp++;
+      }
+    } else if (j - i > 1) {
       if (out) {
         DevSubPath sp;
         sp.draw = draw_index;
@@ -934,7 +955,7 @@ int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_ind
 }
 
 // Split the node list at every move_to and append nodes + sub-path records to the batch.
-int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n, bool allow_parallel) {
+int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t n, bool allow_parallel, bool keep_lone) {
   // leading nodes before the first move_to: line_to / curve_to have no current point
   // (fill_plotter.zig:50,53 -> InternalError.InvalidState); a leading close_path is a no-op.
   size_t first = 0;
@@ -946,10 +967,10 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
   const uint32_t base = (uint32_t)c->rec->nodes.n;
   if (!c->rec->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
   uint32_t n_sp = 0, n_par = 0;
-  int rc = split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, nullptr, n_sp, n_par);
+  int rc = split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, nullptr, n_sp, n_par, keep_lone);
   if (rc) return rc;
   if (!c->rec->subpaths.reserve(c->rec->subpaths.n + n_sp)) return Z2D_E_OUT_OF_MEMORY;
-  split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, c->rec->subpaths.p + c->rec->subpaths.n, n_sp, n_par);
+  split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, c->rec->subpaths.p + c->rec->subpaths.n, n_sp, n_par, keep_lone);
   c->rec->subpaths.n += n_sp;
   c->rec->n_par_sp += n_par;
   return Z2D_OK;
@@ -1325,7 +1346,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   const size_t save_nodes = c->rec->nodes.n, save_sp = c->rec->subpaths.n, save_st = c->rec->strokes.size(), save_src = c->rec->srcs.size();
   const uint32_t di = (uint32_t)c->rec->draws.n;
   const uint32_t save_par = c->rec->n_par_sp;
-  rc = record_nodes(c, di, nodes, n, d.kind == 0 && d.mode == 0);
+  rc = record_nodes(c, di, nodes, n, d.kind == 0 && d.mode == 0, d.kind == 1 && d.dash_count > 0 && d.cap != Z2D_CAP_BUTT);
   DrawIn in;
   in.surface = d.surface;
   in.opts = pack_draw_opts(d.kind, d.aa, d.rule, d.op, d.precision, d.reduces, d.mode);
