@@ -1,0 +1,103 @@
+"""Randomised fills through z2d_submit against the CPU oracle, byte for byte.
+
+A batch of a few hundred painter.fill calls mixes what the spec scenes show one at a time: several sub-paths per call, lines and
+curves, repeated points, two-point "polygons" (move_to, line_to, close_path: the unpaired-crossing quirk of
+fill_plotter.zig:78-81 / multisample.zig:156), empty sub-paths, the trailing move_to Path.close leaves behind, shapes hanging
+over the surface edge, both fill rules, several tolerances and operators.  Some calls qualify for the node-parallel flattening
+kernels and some do not, and one batch holds both (the parallel recorder takes runs of plain fills; here runs are short, so
+both recorders are exercised by the two batch sizes).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.oracle_backend import load_oracle, render_scene
+from z2d_b200 import abi, workloads
+from z2d_b200.abi import AntiAliasMode, Format, NodeTag
+from z2d_b200.host import Surface
+
+pytestmark = pytest.mark.gpu
+
+SIZE = 320
+
+
+def fuzz_scene(seed, n_paths, aa):
+    rng = np.random.default_rng(seed)
+    tags, pts, node_off = [], [], [0]
+
+    def q(v):
+        return float(np.round(v * 16) / 16)
+
+    for _ in range(n_paths):
+        for _sub in range(int(rng.integers(1, 4))):
+            x, y = rng.uniform(-20, SIZE + 20, 2)
+            x0, y0 = x, y
+            tags.append(int(NodeTag.move_to)); pts.append((q(x), q(y), 0, 0, 0, 0))
+            for _k in range(int(rng.choice([0, 1, 2, 3, 3, 4, 6, 9]))):
+                kind = rng.integers(0, 10)
+                if kind == 0:
+                    tags.append(int(NodeTag.line_to)); pts.append((q(x), q(y), 0, 0, 0, 0))
+                    continue
+                step = rng.uniform(-70, 70, (3, 2))
+                if kind < 6:
+                    x, y = x + step[0, 0], y + step[0, 1]
+                    if kind == 1:
+                        y = pts[-1][1] if tags[-1] != int(NodeTag.curve_to) else pts[-1][5]  # horizontal edge
+                    tags.append(int(NodeTag.line_to)); pts.append((q(x), q(y), 0, 0, 0, 0))
+                else:
+                    c1 = (x + step[0, 0], y + step[0, 1])
+                    c2 = (c1[0] + step[1, 0], c1[1] + step[1, 1])
+                    x, y = c2[0] + step[2, 0], c2[1] + step[2, 1]
+                    tags.append(int(NodeTag.curve_to)); pts.append((q(c1[0]), q(c1[1]), q(c2[0]), q(c2[1]), q(x), q(y)))
+            tags.append(int(NodeTag.close_path)); pts.append((0, 0, 0, 0, 0, 0))  # painter.fill requires closed sub-paths
+            if rng.integers(0, 2) == 0:
+                tags.append(int(NodeTag.move_to)); pts.append((q(x0), q(y0), 0, 0, 0, 0))
+        node_off.append(len(tags))
+    nodes = np.zeros(len(tags), dtype=workloads.NODE_DT)
+    nodes["tag"] = np.array(tags, dtype=np.uint32)
+    nodes["p"] = np.array(pts, dtype=np.float64)
+    patterns = workloads._premultiplied_colours(rng, n_paths)
+    fo = np.zeros(n_paths, dtype=workloads.FILLOPTS_DT)
+    fo["anti_aliasing_mode"] = int(aa)
+    fo["fill_rule"] = rng.integers(0, 2, n_paths)
+    fo["op"] = rng.choice([int(abi.Operator.src_over)] * 6 + [int(abi.Operator.src), int(abi.Operator.xor), int(abi.Operator.multiply),
+                                                             int(abi.Operator.dst_out)], n_paths)
+    fo["precision"] = int(abi.Precision.integer)
+    fo["tolerance"] = rng.choice([0.1, 0.1, 0.01, 0.5, 2.0], n_paths)
+    kind = np.zeros(n_paths, dtype=np.uint32)
+    return workloads.Scene(SIZE, SIZE, nodes, np.array(node_off, dtype=np.int64), patterns, kind, fo,
+                           np.zeros(0, dtype=workloads.STROKEOPTS_DT), np.arange(n_paths, dtype=np.int64))
+
+
+# Open at the end of round 1 ("open parity issues"): one or two fills per failing scene differ.  Root causes
+# seen with tools/fill_fuzz_bisect.py / fill_fuzz_draw.py:
+#  * the unpaired-crossing quirk (a two-point "polygon" leaves a lone edge, multisample.zig:156): the reference pairs that edge's
+#    crossing with the next 0 <-> non-0 transition even when it lies beyond the right edge of the surface and then fills the row up
+#    to the edge; the device path culls edges right of the surface, so the crossing stays unpaired and is dropped (seed 32, fill 273);
+#  * anti-aliasing none, several sub-paths in one call: on two rows the span between a crossing of one sub-path and a crossing of
+#    another is missing on the device (seed 31, fill 154).
+# The combinations below are expected failures until those are fixed; the others must match exactly.
+OPEN = {(31, "none"), (32, "default"), (32, "none"), (32, "supersample_4x"), (33, "default"), (33, "none"), (33, "supersample_4x"),
+        (34, "none")}
+CASES = [pytest.param(seed, n, aa, id=f"{seed}-{n}-{aa.name}",
+                      marks=[pytest.mark.xfail(strict=False, reason="open parity issue, see comment")] if (seed, aa.name) in OPEN else [])
+         for seed, n in [(31, 300), (32, 300), (33, 300), (34, 3000)]
+         for aa in [AntiAliasMode.default, AntiAliasMode.none, AntiAliasMode.supersample_4x]]
+
+
+@pytest.mark.parametrize("seed,n_paths,aa", CASES)
+def test_random_fills_match_oracle(cuda, seed, n_paths, aa):
+    scene = fuzz_scene(seed, n_paths, aa)
+    sfc = Surface(Format.rgba, SIZE, SIZE, None, cuda)
+    cmds = scene.draw_cmds(sfc.handle)
+    statuses = np.zeros(scene.n, dtype=np.int32)
+    cuda._check(cuda.lib.z2d_submit(cuda.ctx, cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), scene.n,
+                                    statuses.ctypes.data_as(C.POINTER(C.c_int32))))
+    assert (statuses == 0).all(), f"statuses {np.unique(statuses)}"
+    got = sfc.download()
+    ref = render_scene(load_oracle(fast=True), scene)
+    sfc.deinit()
+    bad = int((got.reshape(-1, 4) != ref.reshape(-1, 4)).any(axis=1).sum())
+    assert bad == 0, f"{bad} pixels differ from the oracle"
+    assert int((ref.reshape(-1, 4)[:, 3] > 0).sum()) > SIZE * SIZE // 4
