@@ -72,9 +72,10 @@ def fuzz_scene(seed, n_paths, aa):
 
 # Open at the end of round 1 ("open parity issues"): one or two fills per failing scene differ.  Root causes
 # seen with tools/fill_fuzz_bisect.py / fill_fuzz_draw.py:
-#  * the unpaired-crossing quirk (a two-point "polygon" leaves a lone edge, multisample.zig:156): the reference pairs that edge's
-#    crossing with the next 0 <-> non-0 transition even when it lies beyond the right edge of the surface and then fills the row up
-#    to the edge; the device path culls edges right of the surface, so the crossing stays unpaired and is dropped (seed 32, fill 273);
+#  * the unpaired-crossing quirk (a two-point "polygon" leaves a lone edge, multisample.zig:156) together with a shape whose
+#    crossings lie beyond the right edge of the surface: the reference pairs the lone edge's crossing (left of the surface) with the
+#    shape's first 0 <-> non-0 transition and fills six whole rows; the device leaves them empty (seed 32, fill 273; each sub-path
+#    alone matches; cause not yet established -- drop_open_tail in raster.cuh is the place to look);
 #  * anti-aliasing none, several sub-paths in one call: on two rows the span between a crossing of one sub-path and a crossing of
 #    another is missing on the device (seed 31, fill 154).
 # The combinations below are expected failures until those are fixed; the others must match exactly.
