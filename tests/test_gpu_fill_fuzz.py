@@ -72,10 +72,11 @@ def fuzz_scene(seed, n_paths, aa):
 
 # Open at the end of round 1 ("open parity issues"): one or two fills per failing scene differ.  Root causes
 # seen with tools/fill_fuzz_bisect.py / fill_fuzz_draw.py:
-#  * the unpaired-crossing quirk (a two-point "polygon" leaves a lone edge, multisample.zig:156) together with a shape whose
-#    crossings lie beyond the right edge of the surface: the reference pairs the lone edge's crossing (left of the surface) with the
-#    shape's first 0 <-> non-0 transition and fills six whole rows; the device leaves them empty (seed 32, fill 273; each sub-path
-#    alone matches; cause not yet established -- drop_open_tail in raster.cuh is the place to look);
+#  * the unpaired-crossing quirk (a two-point "polygon" leaves a lone edge, multisample.zig:156) on sub-scanlines where two
+#    crossings of another sub-path round to the SAME x (the apex of a shape): the reference's result then depends on the order its
+#    sort leaves equal keys in (Polygon.zig:323, pdq: insertion sort for short lists, i.e. edge order) -- "close, then open" pairs
+#    the lone crossing with the apex and fills the row, "open, then close" leaves it unpaired and draws nothing.  The oracle keeps
+#    edge order; the device has no edge order after binning and treats equal crossings as simultaneous (seed 32, fill 273);
 #  * anti-aliasing none, several sub-paths in one call: on two rows the span between a crossing of one sub-path and a crossing of
 #    another is missing on the device (seed 31, fill 154).
 # The combinations below are expected failures until those are fixed; the others must match exactly.
