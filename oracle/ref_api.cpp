@@ -43,6 +43,14 @@ uint64_t z2d_ref_covered_px(int32_t reset) {
   return v;
 }
 
+// Number of times a call reached a `debug.assert` of the reference that does not hold (the reference panics there in safe
+// builds; see ref_stroke.cpp).  Tests use it to keep such calls out of parity comparisons: there is no reference result.
+uint64_t z2d_ref_assert_trips(int32_t reset) {
+  uint64_t v = g_assert_trips;
+  if (reset) g_assert_trips = 0;
+  return v;
+}
+
 static int check_pattern(const z2d_pattern* p) {  // painter.zig:73-79
   if (p->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(p->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
   return Z2D_OK;

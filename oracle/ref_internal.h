@@ -165,6 +165,7 @@ void spline_decompose(Pt a, Pt b, Pt c, Pt d, double tolerance, F&& emit);
 
 void raster_direct(Sfc& s, const Src& pat, Polygon& poly, uint32_t rule, uint32_t op, uint32_t prec);       // raster/direct.zig
 extern uint64_t g_covered_px;
+extern uint64_t g_assert_trips;
 void raster_multisample(Sfc& s, const Src& pat, Polygon& poly, uint32_t rule, uint32_t op, uint32_t prec);  // raster/multisample.zig
 void raster_supersample(Sfc& s, const Src& pat, Polygon& poly, uint32_t rule, uint32_t op, uint32_t prec);  // raster/supersample.zig
 

@@ -8,6 +8,7 @@
 
 namespace zref {
 
+uint64_t g_assert_trips = 0;  // inputs on which the reference's own debug.assert would fire (ref_stroke.cpp)
 uint64_t g_covered_px = 0;  // pixels with coverage > 0 composited by the MSAA rasteriser (benchmark statistic)
 
 // ----------------------------------------------------------------- Polygon

@@ -399,6 +399,7 @@ void join(PlotState& st, uint32_t join_mode, Pt p0, Pt p1, Pt p2, const Contour:
 
 void plot_single(PlotState& st, Pt start, Pt end) {  // stroke_plotter.zig:251-294
   const StrokeParams& o = *st.opts;
+  if (!st.inner.empty()) g_assert_trips++;  // stroke_plotter.zig:254 debug.assert(self.inner.len == 0)
   Face f = Face::init(start, end, o.thickness, o.ctm);
   auto lt = [&](Pt p) { st.plot(st.outer, p, nullptr); };
   f.cap_p0(o.cap, true, st.pen, lt);
@@ -462,6 +463,7 @@ struct Plotter {
     return Z2D_OK;
   }
   void plot_dotted(Pt point) {  // 202-237
+    if (!st.inner.empty()) g_assert_trips++;  // stroke_plotter.zig:211 debug.assert(self.inner.len == 0)
     if (st.opts->cap == Z2D_CAP_ROUND) {
       for (const PenVertex& v : st.pen->v) st.plot(st.outer, {point.x + v.point.x, point.y + v.point.y}, nullptr);
       st.flush(st.outer);
@@ -589,6 +591,10 @@ struct DashedPlotter {
   void plot_dotted(PlotState& s, Pt point, Slope slope) {  // dashed_plotter.zig:369-465 (always on self)
     const StrokeParams& o = *st.opts;
     (void)s;
+    // dashed_plotter.zig:381 `debug.assert(self.inner.len == 0); // should have not been used`: the reference panics here in
+    // Debug / ReleaseSafe builds (the modes its spec suite runs in) and has undefined behaviour in ReleaseFast.  What follows
+    // is the literal continuation; the trip is counted so that tests can tell such calls apart (z2d_ref_assert_trips).
+    if (!st.inner.empty()) g_assert_trips++;
     switch (o.cap) {
       case Z2D_CAP_ROUND:
         for (const PenVertex& v : st.pen->v) st.plot(st.outer, {point.x + v.point.x, point.y + v.point.y}, nullptr);

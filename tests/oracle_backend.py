@@ -39,6 +39,8 @@ def load_oracle(fast=False):
     lib.z2d_ref_surface_put_pixel.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(abi.PixelPOD)]
     lib.z2d_ref_covered_px.restype = C.c_uint64
     lib.z2d_ref_covered_px.argtypes = [C.c_int32]
+    lib.z2d_ref_assert_trips.restype = C.c_uint64
+    lib.z2d_ref_assert_trips.argtypes = [C.c_int32]
     lib.z2d_ref_fill.restype = C.c_int32
     lib.z2d_ref_fill.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]
     lib.z2d_ref_stroke.restype = C.c_int32
@@ -111,14 +113,19 @@ class OracleBackend:
         pass
 
 
-def render_scene(lib, scene, lo=0, hi=None, fmt=int(abi.Format.rgba)):
-    """Replay draws [lo, hi) of a workloads.Scene / FillScene through the CPU oracle; returns the raw surface bytes."""
+def render_scene(lib, scene, lo=0, hi=None, fmt=int(abi.Format.rgba), keep=None, asserting=None):
+    """Replay draws [lo, hi) of a workloads.Scene / FillScene through the CPU oracle; returns the raw surface bytes.
+    keep: boolean mask over [lo, hi) of the draws to replay (default all).  asserting: list that receives the indices
+    (relative to lo) of the draws on which one of the reference's own debug.asserts would fire."""
     hi = scene.n if hi is None else hi
     buf = np.zeros(scene.width * scene.height * 4, dtype=np.uint8)
     cmds = scene.draw_cmds(0, lo, hi)
     P = C.POINTER
     ptr = buf.ctypes.data_as(C.c_void_p)
+    lib.z2d_ref_assert_trips(1)
     for i in range(hi - lo):
+        if keep is not None and not keep[i]:
+            continue
         pat = C.cast(C.c_void_p(int(cmds["pattern"][i])), P(abi.PatternPOD))
         nodes = C.cast(C.c_void_p(int(cmds["nodes"][i])), P(abi.Node))
         if int(cmds["kind"][i]) == 0:
@@ -128,4 +135,6 @@ def render_scene(lib, scene, lo=0, hi=None, fmt=int(abi.Format.rgba)):
             rc = lib.z2d_ref_stroke(ptr, fmt, scene.width, scene.height, pat, nodes, int(cmds["n_nodes"][i]),
                                     C.cast(C.c_void_p(int(cmds["stroke"][i])), P(abi.StrokeOptsPOD)))
         assert rc == 0, f"oracle draw {lo + i} failed with {rc}"
+        if asserting is not None and lib.z2d_ref_assert_trips(1):
+            asserting.append(i)
     return buf

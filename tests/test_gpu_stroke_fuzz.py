@@ -11,10 +11,9 @@ Sizes the oracle renders in a few seconds.
 import numpy as np
 import pytest
 
-from tests.oracle_backend import load_oracle, render_scene
+from tests.fuzz_util import assert_scene_matches
 from z2d_b200 import abi, workloads
 from z2d_b200.abi import AntiAliasMode, Format, NodeTag
-from z2d_b200.host import Surface
 
 pytestmark = pytest.mark.gpu
 
@@ -94,41 +93,19 @@ def fuzz_scene(seed, n_paths, aa):
                            np.zeros(0, dtype=workloads.FILLOPTS_DT), so, np.arange(n_paths, dtype=np.int64), keep=(dash_rows,))
 
 
-# Seeds whose 300 strokes all match, and two seeds that each contain strokes of ONE diverging family, kept as expected failures so
-# that it stays visible: the first dash has zero length (a leading 0 entry, or an offset that lands on a dash
-# boundary), so the plotter saves a one-point "initial polygon", and the node list ends while a later dash with joins is still in
-# progress.  The reference then plots the initial dot first, which resets the main outer contour and throws the buffered outer
-# points of the dash in progress away (finish -> finishInitialDotted -> plotDotted, dashed_plotter.zig:334-345, 455-460); the
-# streaming stroker has already emitted those edges, interleaved with the inner contour's, and cannot take only them back.
-SEEDS_OK = [11, 12, 13, 14, 15, 16, 17, 18, 21, 22, 23, 24]
-SEEDS_KNOWN_DIVERGENT = [19, 20]
+# Every call is compared, with one exception the REFERENCE itself defines: a dashed stroke whose first dash has zero length (a
+# leading 0 entry, or an offset that lands on a dash boundary) saves a one-point "initial polygon"; when the node list then ends
+# while a later dash with joins is still in progress, finish -> finishInitialDotted -> plotDotted runs into
+# `debug.assert(self.inner.len == 0); // should have not been used` (dashed_plotter.zig:381; same assert in stroke_plotter.zig:211,254).
+# In Debug / ReleaseSafe builds -- the modes the reference's spec suite runs in -- z2d panics on such a call; in ReleaseFast the
+# behaviour is undefined.  There is no reference result to match, so the oracle counts the trip (z2d_ref_assert_trips), the call is
+# dropped from both renders and the other 299 strokes of the seed are still compared byte for byte.
+SEEDS = list(range(11, 35))
 AA_MODES = [AntiAliasMode.default, AntiAliasMode.none, AntiAliasMode.supersample_4x]
 
 
 @pytest.mark.parametrize("aa", AA_MODES, ids=lambda a: a.name)
-@pytest.mark.parametrize("seed", SEEDS_OK)
+@pytest.mark.parametrize("seed", SEEDS)
 def test_random_stroke_styles_match_oracle(cuda, seed, aa):
-    _run(cuda, seed, aa)
-
-
-@pytest.mark.xfail(strict=False, reason="zero-length initial dash + dash in progress at the end of the node list (see above)")
-@pytest.mark.parametrize("seed", SEEDS_KNOWN_DIVERGENT)
-def test_random_stroke_styles_known_divergences(cuda, seed):
-    _run(cuda, seed, AntiAliasMode.default)
-
-
-def _run(cuda, seed, aa):
-    import ctypes as C
     scene = fuzz_scene(seed, 300, aa)
-    sfc = Surface(Format.rgba, SIZE, SIZE, None, cuda)
-    cmds = scene.draw_cmds(sfc.handle)
-    statuses = np.zeros(scene.n, dtype=np.int32)
-    cuda._check(cuda.lib.z2d_submit(cuda.ctx, cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), scene.n,
-                                    statuses.ctypes.data_as(C.POINTER(C.c_int32))))
-    assert (statuses == 0).all(), f"statuses {np.unique(statuses)}"
-    got = sfc.download()
-    ref = render_scene(load_oracle(fast=True), scene)
-    sfc.deinit()
-    bad = int((got.reshape(-1, 4) != ref.reshape(-1, 4)).any(axis=1).sum())
-    assert bad == 0, f"{bad} pixels differ from the oracle"
-    assert int((ref.reshape(-1, 4)[:, 3] > 0).sum()) > SIZE * SIZE // 4
+    assert_scene_matches(cuda, scene, min_covered=SIZE * SIZE // 4, max_undefined=3)

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
   if (i >= n_sp) return;
   if (order) i = order[i];
   const DevSubPath sp = sps[i];
+  if (i == 0 || sps[i - 1].draw != sp.draw) draws[sp.draw].sp_first = i;  // sub-paths of a draw are consecutive
   if (sp.flags & kSpNodeParallel) {
     sp_count[i] = 0;
     return;
@@ -546,20 +547,35 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
     rx0 = max(0, x0); ry0 = max(0, y0);
     rx1 = min(x1, W); ry1 = min(y1, H);
     if (rx1 <= rx0 || ry1 <= ry0) return;
-  } else {  // raster/direct.zig:44-49 (bounded operators; unbounded ones take the scanline path)
+  } else if (d.mode == 2) {  // raster/direct.zig with an unbounded operator: every row of the surface, composited from row records
+    rx0 = 0; rx1 = W; ry0 = 0; ry1 = H;
+  } else {  // raster/direct.zig:44-49 (bounded operators)
     const int y0 = clampi((int)floor(top), 0, H - 1), y1 = clampi((int)ceil(bottom), y0, H - 1);
     ry0 = y0; ry1 = y1 + 1;
     rx0 = clampi((int)floor(left) - 1, 0, W);
     rx1 = clampi((int)ceil(right) + 1, rx0, W);
     if (rx1 <= rx0) return;
   }
+  const int ry0c = ry0, ry1c = ry1;  // region rows of the canvas (a band surface clips below)
   // band surface: keep the part of the region that falls on the rows this surface holds
   ry0 = max(ry0, s.y0);
   ry1 = min(ry1, s.y0 + s.h);
-  const bool whole = unbounded && d.aa != Z2D_AA_NONE;  // the whole surface is touched (pre-clears / every pixel composited)
+  const bool rowrec = d.mode == 2;
+  const bool whole = (unbounded && d.aa != Z2D_AA_NONE) || rowrec;  // the whole surface is touched (pre-clears / every pixel composited)
   if (ry1 <= ry0 && !whole) return;
   d.rx0 = rx0; d.rx1 = rx1; d.ry0 = ry0; d.ry1 = ry1;
-  if (ry1 > ry0) {
+  if ((rowrec || (d.flags & kDrawUnpaired)) && ry1c > ry0c) {
+    // the outcome depends on the order the reference's sort leaves equal crossings in: k_edge_sim replays its scanline loop
+    const int S = d.aa == Z2D_AA_NONE ? 1 : 4;
+    d.sim_y0 = ry0c * S;
+    d.sim_rows = (ry1c - ry0c) * S;
+    d.sim_base = (uint32_t)atomicAdd(&counters[4], (unsigned long long)d.sim_rows);
+    d.sim_scratch = (uint32_t)atomicAdd(&counters[5], (unsigned long long)d.n_edges);
+  }
+  if (rowrec) {  // no edges are binned: the row records carry the spans
+    d.ey0 = 1;
+    d.ey1 = 0;
+  } else if (ry1 > ry0) {
     d.ey0 = ry0 >> kTileShift;  // canvas tile rows (edge binning)
     d.ey1 = (ry1 - 1) >> kTileShift;
   } else {
@@ -593,7 +609,9 @@ __global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws
   h.ey0 = d.ey0; h.ey1 = d.ey1;
   h.band_base = d.band_base; h.unbounded = d.unbounded;
   h.pre_y0 = d.pre_y0; h.pre_y1 = d.pre_y1; h.pre_x = d.pre_x; h.pre_rows = d.pre_rows;
-  h.flags = d.flags; h._pad[0] = h._pad[1] = h._pad[2] = 0;
+  h.flags = (d.flags & kDrawUnpaired) | (d.mode == 2 ? kDrawRowRecords : 0u);
+  if (d.sim_rows <= 0) h.flags = 0;
+  h.sim_base = d.sim_base; h.sim_y0 = d.sim_y0; h.sim_rows = d.sim_rows;
   hots[i] = h;
 }
 
@@ -621,7 +639,7 @@ __global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* _
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
   const DevDraw& d = draws[edge_draw[i]];
-  if (!d.valid) return;
+  if (!d.valid || d.mode == 2) return;
   int t0, t1;
   if (!edge_band_range(edges[i], d, t0, t1)) return;
   for (int t = t0; t <= t1; t++) atomicAdd(&band_count[d.band_base + (uint32_t)(t - d.ey0)], 1u);
@@ -633,7 +651,7 @@ __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t*
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
   const DevDraw& d = draws[edge_draw[i]];
-  if (!d.valid) return;
+  if (!d.valid || d.mode == 2) return;
   const DevEdge e = edges[i];
   int t0, t1;
   if (!edge_band_range(e, d, t0, t1)) return;
@@ -656,6 +674,97 @@ __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t*
     const uint32_t slot = band_off[b] + atomicAdd(&band_cursor[b], 1u);
     band_edges[slot] = e;
     band_hdr[slot] = h;
+  }
+}
+
+
+// =====================================================================================
+// Exact scanline replay for order-dependent draws.  The reference keeps ONE edge array per polygon, partitions the active
+// edges to its front at every y-breakpoint (rescan, tess/Polygon.zig:275-299) and re-sorts that prefix by x on every
+// scanline with edges and x values moving together (sort, 311-324).  Equal crossings therefore keep the order the previous
+// scanlines left them in (pdq sorts slices of up to 12 elements by insertion, i.e. stably; beyond that its tie order is not
+// pinned by anything in the reference and insertion order is used here too).  That order decides which crossing the
+// non-zero filter (326-353) keeps, so it is visible wherever the crossings of a row do not pair up:
+//   * a fill with a dangling edge (kDrawUnpaired): "for (0..filtered.len / 2)" drops the trailing unmatched crossing
+//     (multisample.zig:156, supersample.zig, direct.zig) -- row record .x = the x of the dropped crossing (INT_MAX: none);
+//   * direct.zig with an unbounded operator (mode 2): every pair clears the rest of its row (direct.zig:112-124), so only the
+//     last processed pair survives -- row record = {start, end of that pair, pairs processed, filtered crossings}.
+// One thread per such draw (rare, degenerate or special-purpose calls); rescanning on every row is equivalent to the
+// reference's breakpoint schedule because a rescan that changes nothing swaps nothing.
+// =====================================================================================
+__global__ void k_edge_sim(const DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
+                           const DevEdge* __restrict__ edges, const uint32_t* __restrict__ sp_off, uint32_t* __restrict__ perm_all,
+                           int32_t* __restrict__ xs_all, int4* __restrict__ rows_all) {
+  const uint32_t di = blockIdx.x * blockDim.x + threadIdx.x;
+  if (di >= n_draws) return;
+  const DevDraw& d = draws[di];
+  if (!d.valid || d.sim_rows <= 0) return;
+  const DevEdge* E = edges + sp_off[d.sp_first];
+  const uint32_t n = d.n_edges;
+  uint32_t* perm = perm_all + d.sim_scratch;
+  int32_t* xs = xs_all + d.sim_scratch;
+  int4* rows = rows_all + d.sim_base;
+  const bool even_odd = d.rule == Z2D_FILL_EVEN_ODD, pair_mode = d.mode == 2;
+  const int W = sfcs[d.surface].w;
+  for (uint32_t k = 0; k < n; k++) perm[k] = k;
+  for (int r = 0; r < d.sim_rows; r++) {
+    const double mid = (double)(d.sim_y0 + r) + 0.5;
+    uint32_t na = 0;
+    for (uint32_t from = 0; from < n; from++) {  // rescan: swap-partition, exactly as the reference does it
+      const DevEdge e = E[perm[from]];
+      const double top = e.y0 < e.y1 ? e.y0 : e.y1, bottom = e.y0 < e.y1 ? e.y1 : e.y0;
+      if (top < mid && bottom >= mid) {
+        if (from != na) {
+          const uint32_t t = perm[na];
+          perm[na] = perm[from];
+          perm[from] = t;
+        }
+        na++;
+      }
+    }
+    for (uint32_t k = 0; k < na; k++) {  // inc
+      const DevEdge e = E[perm[k]];
+      const double top = e.y0 < e.y1 ? e.y0 : e.y1;
+      xs[k] = __double2int_rz(round_half_away(e.x_start + (e.x_inc * (mid - top))));
+    }
+    for (uint32_t a = 1; a < na; a++) {  // sort (insertion: stable)
+      const int32_t key = xs[a];
+      const uint32_t pk = perm[a];
+      uint32_t b = a;
+      while (b > 0 && xs[b - 1] > key) {
+        xs[b] = xs[b - 1];
+        perm[b] = perm[b - 1];
+        b--;
+      }
+      xs[b] = key;
+      perm[b] = pk;
+    }
+    uint32_t nf = na;
+    if (!even_odd) {  // filter: keep 0 -> non-zero and non-zero -> 0 transitions
+      int wind = 0;
+      nf = 0;
+      for (uint32_t from = 0; from < na; from++) {
+        const DevEdge e = E[perm[from]];
+        const int dir = e.y0 < e.y1 ? -1 : 1;
+        xs[nf] = xs[from];
+        const bool was_zero = wind == 0;
+        wind += dir;
+        if (was_zero || wind == 0) nf++;
+      }
+    }
+    if (!pair_mode) {
+      rows[r] = make_int4((nf & 1u) ? xs[nf - 1] : INT_MAX, 0, 0, 0);
+    } else {  // direct.zig:94-124
+      int n_pairs = 0, last_sx = 0, last_ex = 0;
+      for (uint32_t p = 0; p < nf / 2; p++) {
+        const int sx = max(0, xs[2 * p]);
+        if (sx >= W) break;
+        last_sx = sx;
+        last_ex = clampi(xs[2 * p + 1], sx, W);
+        n_pairs++;
+      }
+      rows[r] = make_int4(last_sx, last_ex, n_pairs, (int)min(nf, 0x7fffffffu));
+    }
   }
 }
 
@@ -893,12 +1002,6 @@ void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw
                      uint32_t node_end, const double* dashes, const GradTables& T, cudaStream_t st) {
   k_hairline<<<1, 32, 0, st>>>(sfcs, draws, draw_index, nodes, node_begin, node_end, dashes, T);
 }
-void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const DevEdge* edges, uint32_t n_edges,
-                             int rows, const GradTables& T, cudaStream_t st) {
-  if (rows <= 0) return;
-  k_direct_unbounded<<<(rows + 63) / 64, 64, 0, st>>>(sfcs, draws, draw_index, edges, n_edges, T);
-}
-
 void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, uint32_t* sp_count, const void* pens,
                           const double* dashes, const uint32_t* order, cudaStream_t st) {
   if (n_sp) k_flatten_count<<<blocks_for(n_sp, Z2D_FLATTEN_THREADS), Z2D_FLATTEN_THREADS, 0, st>>>(sps, n_sp, nodes, draws, sp_count, (const PenV*)pens, dashes, order);
@@ -948,6 +1051,10 @@ void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const
     k_band_lists<true><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
   else
     k_band_lists<false><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
+}
+void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
+                     uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {
+  if (n_draws) k_edge_sim<<<blocks_for(n_draws, 64), 64, 0, st>>>(draws, n_draws, sfcs, edges, sp_off, perm, xs, rows);
 }
 void launch_raster(const RasterArgs& A, cudaStream_t st) {
   if (A.n_tiles) k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);

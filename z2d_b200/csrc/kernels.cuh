@@ -24,6 +24,7 @@ struct RasterArgs {
   const DevEdge* band_edges;
   const int4* band_hdr;        // per binned edge: {xlo, xhi, first row | dir<<31, last row}
   unsigned long long* counters;  // [0] covered pixels, [1] region pixels (may be null)
+  const int4* sim_rows;        // row records of k_edge_sim (draws flagged kDrawUnpaired / kDrawRowRecords)
   GradTables T;
 };
 
@@ -69,12 +70,13 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
 // chunk_base[s] = number of (surface, kDrawChunk-draw chunk) blocks before surface s; one block per chunk
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
                        uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
+// exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
+void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
+                     uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);
 void launch_raster(const RasterArgs& A, cudaStream_t st);
 // isolated single-draw modes (slowpath.cuh)
 void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const z2d_node* nodes, uint32_t node_begin,
                      uint32_t node_end, const double* dashes, const GradTables& T, cudaStream_t st);
-void launch_direct_unbounded(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const DevEdge* edges, uint32_t n_edges,
-                             int rows, const GradTables& T, cudaStream_t st);
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st);
 struct ExportArgs {  // z2d_surface_export
   const uint8_t* data;

@@ -320,43 +320,18 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
 }
 
 // Draws flagged kDrawUnpaired only.  The reference pairs the sorted (filtered) crossings of a scanline and drops a
-// trailing unmatched one ("for (0..filtered_edge_set.len / 2)", multisample.zig / supersample.zig / direct.zig), so
-// the inside run that would extend to +infinity is not drawn: clear every sample at or right of the crossing that
-// opens it.  even-odd: the largest crossing; non-zero: the largest crossing with zero winding left of it.
-__device__ __noinline__ uint64_t drop_open_tail(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys, int sx0,
-                                                int ncols, bool even_odd, uint64_t m) {
-  int total = 0, n = 0;
-  for (uint32_t i = 0; i < n_be; i++) {
-    const int4 h = __ldg(hd + i);
-    if (!hdr_active(h, ys)) continue;
-    total += h.z < 0 ? 1 : -1;
-    n++;
-  }
-  if (even_odd ? !(n & 1) : total == 0) return m;
-  const double mid = (double)ys + 0.5;
-  double x_cut = -INFINITY;
-  for (uint32_t j = 0; j < n_be; j++) {
-    const int4 hj = __ldg(hd + j);
-    if (!hdr_active(hj, ys)) continue;
-    const double4 ej = ld_edge(be + j);
-    const double xj = round_half_away(ej.z + (ej.w * (mid - (hj.z < 0 ? ej.y : ej.x))));
-    if (!(xj > x_cut)) continue;
-    if (!even_odd) {
-      int before = 0;
-      for (uint32_t i = 0; i < n_be; i++) {
-        const int4 hi = __ldg(hd + i);
-        if (!hdr_active(hi, ys)) continue;
-        const double4 ei = ld_edge(be + i);
-        const double xi = round_half_away(ei.z + (ei.w * (mid - (hi.z < 0 ? ei.y : ei.x))));
-        if (xi < xj) before += hi.z < 0 ? 1 : -1;
-      }
-      if (before != 0) continue;
-    }
-    x_cut = xj;
-  }
-  const double cf = x_cut - (double)sx0;
-  if (!(cf < (double)ncols)) return m;
-  if (cf <= 0.0) return 0ull;
+// trailing unmatched one ("for (0..filtered_edge_set.len / 2)", multisample.zig:156 / supersample.zig / direct.zig), so
+// the inside run that would extend to +infinity is not drawn.  Which crossing that is depends on the order the
+// reference's sort leaves equal crossings in; k_edge_sim (kernels.cu) replays the reference's scanline loop for these
+// draws and records the x of the dropped crossing per (sub-)scanline: clear every sample at or right of it.
+Z2D_D uint64_t cut_open_tail(const RasterArgs& A, const DrawHot& h, int ys, int sx0, int ncols, uint64_t m) {
+  const int r = ys - h.sim_y0;
+  if (r < 0 || r >= h.sim_rows) return m;
+  const int cut = __ldg(&A.sim_rows[h.sim_base + (uint32_t)r]).x;
+  if (cut == INT_MAX) return m;
+  const long long cf = (long long)cut - (long long)sx0;
+  if (cf >= (long long)ncols) return m;
+  if (cf <= 0) return 0ull;
   return m & ~(~0ull << (int)cf);
 }
 
@@ -456,7 +431,8 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
       const bool in_rows = ty >= h.ey0 && ty <= h.ey1;
       const bool pre = h.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
       const bool all_px = aa == Z2D_AA_SUPERSAMPLE_4X;  // every pixel of the region is composited, even at coverage 0
-      if (!in_rows && !pre) continue;
+      const bool rowrec = (h.flags & kDrawRowRecords) != 0u;
+      if (!in_rows && !pre && !rowrec) continue;
       n_pairs++;
       if (in_rows) {
         const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
@@ -469,8 +445,8 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         if (Sc == 4) {
           tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, wdiff_s[warp], m0, m1, n_eval);
           if (h.flags & kDrawUnpaired) {
-            m0 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m0);
-            m1 = drop_open_tail(be, hd, nbe, ty * kTile * 4 + lane * 2 + 1, sx0, 64, h.rule == Z2D_FILL_EVEN_ODD, m1);
+            m0 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2, sx0, 64, m0);
+            m1 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2 + 1, sx0, 64, m1);
           }
           // pixel row `row` needs sub-scanlines 4*row .. 4*row+3: this lane's two and its partner's two
           const uint64_t q0 = __shfl_xor_sync(0xffffffffu, m0, 1), q1 = __shfl_xor_sync(0xffffffffu, m1, 1);
@@ -481,7 +457,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
           tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, wdiff_s[warp], m0, m1, n_eval);
-          if (h.flags & kDrawUnpaired) m0 = drop_open_tail(be, hd, nbe, ty * kTile + row, sx0, 16, h.rule == Z2D_FILL_EVEN_ODD, m0);
+          if (h.flags & kDrawUnpaired) m0 = cut_open_tail(A, h, ty * kTile + row, sx0, 16, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
             cov_e |= ((bits >> i) & 1u) << (4 * i);  // byte i/2
@@ -490,7 +466,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         }
       }
       // nothing of this draw lands in the tile?
-      const bool lane_work = row_ok && (pre || (py >= h.ry0 && py < h.ry1 && (all_px || (cov_e | cov_o) != 0u)));
+      const bool lane_work = row_ok && (pre || rowrec || (py >= h.ry0 && py < h.ry1 && (all_px || (cov_e | cov_o) != 0u)));
       if (!__any_sync(0xffffffffu, lane_work)) continue;
 
       if (!loaded) {  // lazy tile load: 8 pixels per lane
@@ -509,6 +485,32 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
 
       // ---- composite the lane's 8 pixels
       const RGBA16 spx = unpack_rgba(h.px_rgba);
+      if (rowrec) {
+        // direct.zig with an unbounded operator (anti-aliasing none): every row of the surface is rewritten from its row
+        // record {start, end of the last processed span pair, pairs processed, filtered crossings} (k_edge_sim; direct.zig:88-124)
+        const int rr = py - h.sim_y0;
+        if (row_ok && rr >= 0 && rr < h.sim_rows) {
+          const int4 rec = __ldg(&A.sim_rows[h.sim_base + (uint32_t)rr]);
+          if (rec.w == 0 || rec.z > 0) {  // (crossings but no pair processed: the row is left untouched)
+            const DevDraw& dd = A.draws[di];
+#pragma unroll 1
+            for (int i = 0; i < 8; i++) {
+              const int x = px0 + i;
+              if (x >= S.w) break;
+              uint32_t raw = 0u;  // cleared: a row without crossings, or outside the surviving pair
+              if (rec.w != 0 && x >= rec.x && x < rec.y) {
+                if (rec.z == 1) raw = px[Z2D_PXI(i)];  // (a later pair composites over what the previous pair's tail clear left)
+                n_cov++;
+                raw = composite_cov(h, dd, A.T, tf, spx, raw, 1, x, py);
+              }
+              px[Z2D_PXI(i)] = raw;
+            }
+          }
+        }
+        __syncwarp();
+        dirty = true;
+        continue;
+      }
       if (tf.is32 && h.src_kind == Z2D_PARAM_PIXEL && h.op == Z2D_OP_SRC_OVER && !pre && !all_px &&
           (h.reduces || h.precision == Z2D_PRECISION_INTEGER)) {
         // fast path: single-pixel source, integer src_over.  Lanes 1..16 build the source at each coverage level

@@ -4,10 +4,8 @@
 //   k_hairline          raster/hairline.zig + tess/polyline_plotter.zig: 1-pixel Bresenham / Wu lines.
 //                       Pixels shared by consecutive segments are composited twice, in order, so a
 //                       draw is walked sequentially by one thread (hairline draws are tiny).
-//   k_direct_unbounded  raster/direct.zig with an unbounded operator (src_in, dst_in, src_out,
-//                       dst_atop) and anti-aliasing off: every span pair clears the rest of its
-//                       scanline (direct.zig:112-124), so the outcome of a row depends on ALL its
-//                       crossings; one thread per scanline replays the reference's pair loop.
+// (raster/direct.zig with an unbounded operator, once isolated too, now runs in the tile pipeline from the row records of
+// k_edge_sim, kernels.cu.)
 #pragma once
 
 namespace z2d {
@@ -250,93 +248,6 @@ __global__ void k_hairline(const DevSurface* __restrict__ sfcs, const DevDraw* _
     }
   }
   if (c_len != 0) contour_end();
-}
-
-// ---------------------------------------------------------------------------------------------
-// direct.zig, unbounded operator: one thread per scanline, all edges of the (single) draw.
-__global__ void k_direct_unbounded(const DevSurface* __restrict__ sfcs, const DevDraw* __restrict__ draws, uint32_t draw_index,
-                                   const DevEdge* __restrict__ edges, uint32_t n_edges, GradTables T) {
-  const DevDraw& d = draws[draw_index];
-  const DevSurface S = sfcs[d.surface];
-  const int yl = blockIdx.x * blockDim.x + threadIdx.x;  // row of this surface; y: row of the canvas
-  if (yl >= S.h) return;
-  const int y = yl + S.y0;
-  const int W = S.w;
-  {  // direct.zig:57-67: no y-breakpoint at or below scanline 0 => the whole draw is a no-op
-    bool any = false;
-    for (uint32_t i = 0; i < n_edges; i++) any |= round_half_away(fmax(edges[i].y0, edges[i].y1)) >= 0.0;
-    if (!any) return;
-  }
-  const double ym = (double)y + 0.5;
-  const bool even_odd = d.rule == Z2D_FILL_EVEN_ODD;
-
-  // Walk the crossings of this scanline in ascending (x, edge index) order without storing them and
-  // replay WorkingEdgeSet.filter + the pair loop (Polygon.zig:326-353, direct.zig:88-124).  Net effect
-  // of the pair loop: every processed pair clears the whole row outside its own span, so only the LAST
-  // processed pair survives; it composites over the original pixels iff it is also the first one.
-  int prev_x = INT_MIN;
-  int prev_i = -1;
-  int wind = 0;
-  int n_filtered = 0;     // filtered crossings seen so far
-  int pair_start = 0;     // pending pair start (valid when n_filtered is odd)
-  int n_pairs = 0;        // processed pairs
-  int last_sx = 0, last_ex = 0;
-  bool stop = false;
-  while (!stop) {
-    int best_x = INT_MAX, best_i = -1, best_dir = 0;
-    for (uint32_t i = 0; i < n_edges; i++) {
-      const DevEdge e = edges[i];
-      const bool down = e.y0 < e.y1;
-      const double top = down ? e.y0 : e.y1, bottom = down ? e.y1 : e.y0;
-      if (!(top < ym && ym <= bottom)) continue;
-      const int x = (int)round_half_away(e.x_start + (e.x_inc * (ym - top)));
-      if (x < prev_x || (x == prev_x && (int)i <= prev_i)) continue;
-      if (x < best_x || (x == best_x && (int)i < best_i)) {
-        best_x = x;
-        best_i = (int)i;
-        best_dir = down ? -1 : 1;
-      }
-    }
-    if (best_i < 0) break;
-    prev_x = best_x;
-    prev_i = best_i;
-    bool keep;
-    if (even_odd) {
-      keep = true;
-    } else {
-      const int before = wind;
-      wind += best_dir;
-      keep = (before == 0) || (wind == 0);
-    }
-    if (!keep) continue;
-    if ((n_filtered & 1) == 0) {
-      pair_start = best_x;
-    } else {
-      const int sx = max(0, pair_start);
-      if (sx >= W) {
-        stop = true;  // direct.zig:99-102 break
-      } else {
-        last_sx = sx;
-        last_ex = max(sx, min(best_x, W));
-        n_pairs++;
-      }
-    }
-    n_filtered++;
-  }
-  if (n_filtered == 0) {  // direct.zig:88-92
-    for (int x = 0; x < W; x++) store_raw(S.data, S.fmt, (size_t)yl * W + x, 0u);
-    return;
-  }
-  if (n_pairs == 0) return;  // nothing processed: the row is left untouched
-  for (int x = 0; x < W; x++) {
-    const size_t idx = (size_t)yl * (size_t)W + (size_t)x;
-    if (x >= last_sx && x < last_ex) {
-      if (n_pairs > 1) store_raw(S.data, S.fmt, idx, 0u);  // cleared by the previous pair's tail clear
-      px_composite(S, d, T, x, y, false, 255);
-    } else {
-      store_raw(S.data, S.fmt, idx, 0u);
-    }
-  }
 }
 
 }  // namespace z2d

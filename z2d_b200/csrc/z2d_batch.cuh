@@ -77,9 +77,17 @@ struct DevDraw {
   int32_t pre_y0, pre_y1, pre_x, pre_rows;  // MSAA unbounded pre-clear (multisample.zig:96-110)
   uint32_t band_base;           // first (draw, tile-row) slot
   uint32_t unbounded;
+  // exact scanline replay (k_edge_sim) for draws whose result depends on the ORDER of equal crossings: fills with a dangling
+  // edge (kDrawUnpaired) and the direct rasteriser with an unbounded operator (mode 2)
+  uint32_t sp_first;            // first sub-path of the draw (its edges start at sp_off[sp_first], in plotting order)
+  uint32_t sim_base;            // first row record
+  uint32_t sim_scratch;         // first slot of the per-edge scratch (permutation, x values)
+  int32_t sim_y0, sim_rows;     // (sub-)scanlines [sim_y0, sim_y0 + sim_rows) of the canvas
+  uint32_t _pad1;
 };
 
 constexpr uint32_t kDrawUnpaired = 1u;
+constexpr uint32_t kDrawRowRecords = 2u;  // DrawHot.flags only: mode 2, composited from the row records of k_edge_sim
 
 // What the host uploads per draw call (32 B); k_expand_draws turns it into the DevDraw the other kernels read.
 // Sources other than a single pixel and all stroke parameters live in side tables.
@@ -122,7 +130,9 @@ struct alignas(16) DrawHot {
   int32_t ey0, ey1;
   uint32_t band_base, unbounded;
   int32_t pre_y0, pre_y1, pre_x, pre_rows;
-  uint32_t flags, _pad[3];
+  uint32_t flags;
+  uint32_t sim_base;  // row records of k_edge_sim (kDrawUnpaired / kDrawRowRecords)
+  int32_t sim_y0, sim_rows;
 };
 
 // order-preserving f64 <-> i64 (for atomicMin / atomicMax on extents)

@@ -100,7 +100,7 @@ struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_r
 struct FillPlan {
   int32_t status;
   uint32_t eligible, skip;  // skip: valid call that records nothing (empty node list)
-  uint32_t first, m, n_sp, n_par;
+  uint32_t first, m, n_sp, n_par, all_simple;
   uint32_t node_base, sp_base, draw_idx, slot;
 };
 
@@ -181,6 +181,7 @@ struct z2d_ctx {
   uint32_t* h_total = nullptr;  // pinned readback slot
   DevBuf d_counters, d_boxes, d_hots, d_band_hdr;
   DevBuf d_export, d_gamma;  // z2d_surface_export: scanline staging, sRGB channel table
+  DevBuf d_sim_rows, d_sim_perm, d_sim_x;  // k_edge_sim: row records, per-edge scratch
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   BatchMeta last;
   bool stats_pending = false;
@@ -558,8 +559,11 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + n_cnt, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 2, c->d_list_off.as<uint32_t>() + n_work, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(c->h_total + 4, c->d_counters.as<unsigned long long>() + 4, 16, cudaMemcpyDeviceToHost, st));  // k_edge_sim sizes
   CK(c, cudaStreamSynchronize(st));
   const uint32_t n_edges = c->h_total[0], n_slots = c->h_total[1], n_items = c->h_total[2];
+  const unsigned long long sim_rows = *reinterpret_cast<unsigned long long*>(c->h_total + 4),
+                           sim_slots = *reinterpret_cast<unsigned long long*>(c->h_total + 6);
 
   // K1 (emit half)
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
@@ -574,6 +578,14 @@ int run_pipeline(z2d_ctx* c, bool replay) {
                          c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
                          c->d_edge_draw.as<uint32_t>(), c->d_curve_list.as<uint32_t>(), st);
     launches += 2;
+  }
+  if (sim_rows) {  // order-dependent draws (dangling edges, direct rasteriser with an unbounded operator): exact scanline replay
+    CK(c, c->d_sim_rows.ensure((size_t)sim_rows * sizeof(int4)));
+    CK(c, c->d_sim_perm.ensure((size_t)sim_slots * 4 + 16));
+    CK(c, c->d_sim_x.ensure((size_t)sim_slots * 4 + 16));
+    launch_edge_sim(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, c->d_edges.as<DevEdge>(), c->d_sp_off.as<uint32_t>(),
+                    c->d_sim_perm.as<uint32_t>(), c->d_sim_x.as<int32_t>(), c->d_sim_rows.as<int4>(), st);
+    launches += 1;
   }
   CK(c, cudaEventRecord(c->ev[1], st));
 
@@ -613,6 +625,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.band_edges = c->d_band_edges.as<DevEdge>();
   A.band_hdr = c->d_band_hdr.as<int4>();
   A.counters = c->d_counters.as<unsigned long long>();
+  A.sim_rows = c->d_sim_rows.as<int4>();
   A.T = tables(c, S.grads, S.stop_off, S.stop_col);
   launch_raster(A, st);
   CK(c, cudaGetLastError());
@@ -633,8 +646,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   return Z2D_OK;
 }
 
-// Hairline strokes and the direct rasteriser with an unbounded operator are order / row-globally coupled
-// (slowpath.cuh); they run as a batch of exactly one draw.
+// Hairline strokes are order-coupled per pixel (slowpath.cuh); they run as a batch of exactly one draw.
 int run_isolated(z2d_ctx* c, Batch& B) {
   const BatchMeta& m = c->last;
   InputSet& S = c->in[m.set];
@@ -643,27 +655,8 @@ int run_isolated(z2d_ctx* c, Batch& B) {
   uint32_t launches = 0, n_edges = 0;
   CK(c, cudaEventRecord(c->ev[0], st));
   launch_expand_draws(S.d_draws_in.as<DrawIn>(), S.strokes, S.srcs, c->d_draws.as<DevDraw>(), 1, st);
-  if (B.iso_mode == 1) {
-    launch_hairline(S.sfcs, c->d_draws.as<DevDraw>(), 0, S.d_nodes.as<z2d_node>(), B.iso_node_begin, B.iso_node_end,
-                    S.dashes, T, st);
-    launches = 2;
-  } else {
-    const uint32_t n_sp = m.n_sp;
-    CK(c, c->d_sp_count.ensure((size_t)n_sp * 4 + 16));
-    launch_flatten_count(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>(),
-                         S.pens, S.dashes, nullptr, st);
-    CK(c, c->d_sp_off.ensure(((size_t)n_sp + 1) * 4));
-    CK(c, c->d_scan_tmp.ensure(scan_tmp_len(n_sp) * 4));
-    exclusive_scan(c->d_sp_count.as<uint32_t>(), c->d_sp_off.as<uint32_t>(), n_sp, c->d_scan_tmp.as<uint32_t>(), st);
-    int rc = read_total(c, c->d_sp_off.as<uint32_t>() + n_sp, n_edges);
-    if (rc) return rc;
-    CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
-    CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
-    launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, nullptr, st);
-    launch_direct_unbounded(S.sfcs, c->d_draws.as<DevDraw>(), 0, c->d_edges.as<DevEdge>(), n_edges, B.batch_sfcs[0]->h, T, st);
-    launches = 7;
-  }
+  launch_hairline(S.sfcs, c->d_draws.as<DevDraw>(), 0, S.d_nodes.as<z2d_node>(), B.iso_node_begin, B.iso_node_end, S.dashes, T, st);
+  launches = 2;
   CK(c, cudaGetLastError());
   for (int i = 1; i <= 4; i++) CK(c, cudaEventRecord(c->ev[i], st));
   // the pinned batch arrays are reused by the next draw: their async uploads must have landed (the tile
@@ -800,7 +793,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
                 B.pens.size() * 8 + B.dashes.size() * 8 +
                 sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + B.grads.size() * sizeof(DevGrad) +
                 B.stop_offsets.size() * 4 + B.stop_colors.size() * sizeof(float4);
-  int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) != 0) ? run_isolated(c, B) : run_pipeline(c, false);
+  int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) == 1u) ? run_isolated(c, B) : run_pipeline(c, false);
   cudaEventRecord(S.done, c->stream);  // (also on failure: the set is reusable after whatever was enqueued)
   S.used = true;
   clear_batch(c, B);
@@ -898,10 +891,15 @@ bool is_closed_node_set(const z2d_node* nodes, size_t n) {  // path_nodes.zig:23
 // (dashed_plotter.zig:334-367 and 266-271, plotDotted 369-465), and a square dot is oriented by the slope the plotter last saw
 // -- state that survives move_to (current_slope, dashed_plotter.zig:98).  Such a sub-path is appended to the sub-path before it
 // (one thread plots both, in order) or, at the start of the list, becomes a sub-path of its own.
+//
+// all_simple (optional): every sub-path that draws something qualifies.  A fill call with a sub-path that does not may leave
+// a dangling edge (a two-point "polygon"), whose result depends on the order of the call's edges (k_edge_sim): such a call
+// is recorded with allow_parallel = false, so that all its edges are emitted by the sequential plotter, in plotting order.
 int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_index, bool allow_parallel, DevSubPath* out, uint32_t& n_sp,
-                   uint32_t& n_par, bool keep_lone = false) {
+                   uint32_t& n_par, bool keep_lone = false, bool* all_simple = nullptr) {
   n_sp = 0;
   n_par = 0;
+  if (all_simple) *all_simple = true;
   size_t i = 0;
   while (i < m) {
     size_t j = i + 1;
@@ -948,6 +946,7 @@ int split_subpaths(const z2d_node* q, size_t m, uint32_t base, uint32_t draw_ind
       }
       n_sp++;
       n_par += simple ? 1u : 0u;
+      if (all_simple && !simple) *all_simple = false;
     }
     i = j;
   }
@@ -967,8 +966,10 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
   const uint32_t base = (uint32_t)c->rec->nodes.n;
   if (!c->rec->nodes.append(nodes + first, n - first)) return Z2D_E_OUT_OF_MEMORY;
   uint32_t n_sp = 0, n_par = 0;
-  int rc = split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, nullptr, n_sp, n_par, keep_lone);
+  bool all_simple = true;
+  int rc = split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, nullptr, n_sp, n_par, keep_lone, &all_simple);
   if (rc) return rc;
+  allow_parallel = allow_parallel && all_simple;
   if (!c->rec->subpaths.reserve(c->rec->subpaths.n + n_sp)) return Z2D_E_OUT_OF_MEMORY;
   split_subpaths(nodes + first, n - first, base, draw_index, allow_parallel, c->rec->subpaths.p + c->rec->subpaths.n, n_sp, n_par, keep_lone);
   c->rec->subpaths.n += n_sp;
@@ -1053,6 +1054,9 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   c->d_export.release();
   c->d_gamma.release();
+  c->d_sim_rows.release();
+  c->d_sim_perm.release();
+  c->d_sim_x.release();
   for (InputSet& is : c->in) {
     is.release();
     if (is.done) cudaEventDestroy(is.done);
@@ -1371,7 +1375,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     in.stroke_index = (uint32_t)c->rec->strokes.size();
     c->rec->strokes.push_back(si);
   }
-  if (d.mode != 0) {
+  if (d.mode == 1) {
     c->rec->iso_mode = d.mode;
     c->rec->iso_node_begin = (uint32_t)save_nodes;
     c->rec->iso_node_end = (uint32_t)c->rec->nodes.n;
@@ -1388,7 +1392,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     c->rec->stop_colors.resize(save_c);
     return rc;
   }
-  if (d.mode != 0 || c->rec->nodes.n > kMaxBatchNodes || c->rec->draws.n > kMaxBatchDraws) return flush(c);
+  if (d.mode == 1 || c->rec->nodes.n > kMaxBatchNodes || c->rec->draws.n > kMaxBatchDraws) return flush(c);
   // Pipelined recording: hand the batch to the worker as soon as it is idle (so the device starts early and is fed batches as
   // large as the time it took to execute the previous one), at the latest every chunk_draws draws.  Asynchronous: recording
   // continues into the other batch.
@@ -1416,11 +1420,7 @@ int32_t z2d_fill(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_n
   d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;  // multisample.zig:36, compositor.zig:317-322
   d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
   d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;  // painter.zig:103
-  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {  // direct.zig clears per span pair: row-global, runs isolated
-    d.mode = 2;
-    int frc = flush(c);  // everything recorded so far lands first
-    if (frc) return frc;
-  }
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) d.mode = 2;  // direct.zig clears per span pair: composited from row records
   return record_draw(c, s, pattern, nodes, n, d);
 }
 
@@ -1507,11 +1507,7 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
   d.scale = aa == Z2D_AA_NONE ? 1.0 : 4.0;
   d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;
-  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) {
-    d.mode = 2;
-    int frc = flush(c);
-    if (frc) return frc;
-  }
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) d.mode = 2;
   // painter.zig:287-304: thin lines lose cap / join / miter settings; minimum width 1/256
   const double min_w = 0.00390625;
   d.cap = o->line_width >= 2 ? o->line_cap_mode : (uint32_t)Z2D_CAP_BUTT;
@@ -1554,7 +1550,7 @@ static void plan_fill(z2d_ctx* c, const z2d_draw_cmd& k, FillPlan& pl) {
       o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X)
     return;  // not eligible: the one-by-one path produces the status
   const uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;
-  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) return;  // isolated mode
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) return;  // row-record mode: recorded by z2d_fill
   pl.eligible = 1;
   if (!px_can_demultiply(pat->pixel)) {
     pl.status = Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
@@ -1582,7 +1578,10 @@ static void plan_fill(z2d_ctx* c, const z2d_draw_cmd& k, FillPlan& pl) {
   }
   pl.first = (uint32_t)first;
   pl.m = (uint32_t)(k.n_nodes - first);
-  pl.status = split_subpaths(k.nodes + first, pl.m, 0, 0, true, nullptr, pl.n_sp, pl.n_par);
+  bool all_simple = true;
+  pl.status = split_subpaths(k.nodes + first, pl.m, 0, 0, true, nullptr, pl.n_sp, pl.n_par, false, &all_simple);
+  pl.all_simple = all_simple ? 1u : 0u;
+  if (!all_simple) pl.n_par = 0;
 }
 
 static void write_fill(Batch& B, const z2d_draw_cmd& k, const FillPlan& pl) {
@@ -1591,7 +1590,7 @@ static void write_fill(Batch& B, const z2d_draw_cmd& k, const FillPlan& pl) {
   const z2d_pixel& px = k.pattern->pixel;
   memcpy(B.nodes.p + pl.node_base, k.nodes + pl.first, (size_t)pl.m * sizeof(z2d_node));
   uint32_t n_sp, n_par;
-  split_subpaths(k.nodes + pl.first, pl.m, pl.node_base, pl.draw_idx, true, B.subpaths.p + pl.sp_base, n_sp, n_par);
+  split_subpaths(k.nodes + pl.first, pl.m, pl.node_base, pl.draw_idx, pl.all_simple != 0, B.subpaths.p + pl.sp_base, n_sp, n_par);
   uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;  // as z2d_fill / record_draw
   if (aa == Z2D_AA_DEFAULT) aa = Z2D_AA_MULTISAMPLE_4X;
   const uint32_t precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
