@@ -287,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- compositor kernel roofline (config 4 shape: 8192^2 RGBA8 src_over, single-pixel source)
     comp = None
-    if rank == 0:
+    if rank == 0 and not args.no_composite:
         comp = composite_roofline(cb, args)
 
     # ---- CPU baseline (rank 0, N == 1 only): bounded sample of the same workload
@@ -389,6 +389,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-composite", action="store_true", help="skip the K5 roofline leg (profiling runs)")
     ap.add_argument("--chunk", type=int, default=-1, help="recorder chunk size for the e2e leg (-1: library default, 0: one batch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

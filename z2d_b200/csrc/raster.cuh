@@ -363,12 +363,45 @@ Z2D_D uint32_t src_over_x4(uint32_t raw, uint2 s, uint32_t amask) {
   return (lo | (hi << 8)) & amask;
 }
 
+// ---- table-driven form of the same blend for the tile kernel.  Entry c of the per-(draw, tile) table holds the source at
+// coverage level c in blend-ready form: {C_lo, C_hi, 255 - sa}, C = (source lanes << 8) + the rounding terms of div255_x2
+// so that per pixel, with p = d * inv (+ 254 << 16 in the alpha lane, the IMAD's addend),
+//     q = p + ((p >> 8) & 0x00ff00ff) + C                      (one IMAD, one PRMT, one IADD3 per 16-bit lane pair)
+// and byte 1 / byte 3 of q are the blended channels: s + floor(d * inv / 255) <= 255 for premultiplied sources, so the sum
+// never carries into the neighbouring lane.  Identical results to src_over_x4.  Formats without an alpha channel keep the
+// destination alpha lane at 0 (hmask) and C_hi's alpha lane at 1: a touched pixel gets padding byte 0, as pack32 writes it.
+Z2D_D uint4 blend_entry(const Fmt32& f, RGBA16 s, int m, bool masked) {
+  const uint2 sl = src_lanes(f, s, m, masked);
+  const uint32_t inv = 255u - (sl.y >> 16);
+  const uint32_t hi = f.has_a ? (0x00010001u + (sl.y << 8)) : (0x00010001u + ((sl.y & 0xffu) << 8));
+  return make_uint4(0x00010001u + (sl.x << 8), hi, inv, f.has_a ? (254u << 16) : 0u);  // .w: addend of the alpha lane's product
+}
+Z2D_D uint32_t blend_tab_px(uint32_t raw, const uint4 e, uint32_t hmask) {
+  const uint32_t plo = (raw & 0x00ff00ffu) * e.z, phi = ((raw >> 8) & hmask) * e.z + e.w;
+  const uint32_t qlo = plo + __byte_perm(plo, 0u, 0x4341) + e.x;  // + ((p >> 8) & 0x00ff00ff)
+  const uint32_t qhi = phi + __byte_perm(phi, 0u, 0x4341) + e.y;
+  return __byte_perm(qlo, qhi, 0x7351);  // bytes: qlo.1, qhi.1, qlo.3, qhi.3
+}
+// the lane's 8 pixels (two uint4); cov_e / cov_o: coverage level of the even / odd pixels, one byte each (0: untouched)
+Z2D_D void blend_fast8(uint4& v0, uint4& v1, uint32_t cov_e, uint32_t cov_o, const uint4* __restrict__ tab, uint32_t hmask) {
+#define Z2D_BL(dst, covw, sel)                                                   \
+  {                                                                              \
+    const uint32_t c = __byte_perm(covw, 0u, sel);                               \
+    const uint32_t r = blend_tab_px(dst, tab[c], hmask);                         \
+    if (c) dst = r;                                                              \
+  }
+  Z2D_BL(v0.x, cov_e, 0x4440) Z2D_BL(v0.y, cov_o, 0x4440) Z2D_BL(v0.z, cov_e, 0x4441) Z2D_BL(v0.w, cov_o, 0x4441)
+  Z2D_BL(v1.x, cov_e, 0x4442) Z2D_BL(v1.y, cov_o, 0x4442) Z2D_BL(v1.z, cov_e, 0x4443) Z2D_BL(v1.w, cov_o, 0x4443)
+#undef Z2D_BL
+}
+Z2D_D uint32_t nonzero_bytes(uint32_t x) { return (uint32_t)__popc(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu | x) & 0x80808080u); }
+
 #ifndef Z2D_RASTER_MIN_CTAS
 #define Z2D_RASTER_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(RasterArgs A) {
   __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
-  __shared__ uint2 src_tab[kRasterThreads / 32][17];
+  __shared__ uint4 blend_tab[kRasterThreads / 32][17];
   __shared__ int wdiff_s[kRasterThreads / 32][66];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
@@ -514,33 +547,29 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
       if (tf.is32 && h.src_kind == Z2D_PARAM_PIXEL && h.op == Z2D_OP_SRC_OVER && !pre && !all_px &&
           (h.reduces || h.precision == Z2D_PRECISION_INTEGER)) {
         // fast path: single-pixel source, integer src_over.  Lanes 1..16 build the source at each coverage level
-        // (multisample.zig:223: alpha 16 * cov - 1; full coverage: unmasked), then every lane blends its pixels.
-        uint2* st = src_tab[warp];
-        if (lane >= 1 && lane <= 16) st[lane] = src_lanes(tf.f, spx, 16 * lane - 1, lane < 16);
+        // (multisample.zig:223: alpha 16 * cov - 1; full coverage: unmasked) in blend-ready form, then every lane blends
+        // its 8 pixels straight-line (no divergence between fully and partially covered pixels, no register indexing).
+        uint4* bt = blend_tab[warp];
+        const int full = aa == Z2D_AA_NONE ? 1 : 16;
+        if (lane >= 1 && lane <= full) bt[lane] = blend_entry(tf.f, spx, 16 * lane - 1, lane < full);
         __syncwarp();
-        if (row_ok && py >= h.ry0 && py < h.ry1 && (cov_e | cov_o) != 0u) {
+        if (!(row_ok && py >= h.ry0 && py < h.ry1)) cov_e = cov_o = 0u;
+        {
           const int lo = max(h.rx0 - px0, 0), hi = min(min(h.rx1, S.w) - px0, 8);
-          const uint32_t amask = tf.f.has_a ? 0xffffffffu : 0x00ffffffu;
-          const uint32_t full = aa == Z2D_AA_NONE ? 1u : 16u;
-          uint4 v[2] = {reinterpret_cast<uint4*>(px)[lane], reinterpret_cast<uint4*>(px)[32 + lane]};
-          uint32_t* w = reinterpret_cast<uint32_t*>(v);
-          const uint2 sfull = st[16];
-          if (lo == 0 && hi == 8 && cov_e == full * 0x01010101u && cov_o == cov_e) {  // interior: all 8 pixels fully covered
-            n_cov += 8;
-#pragma unroll 1  // rolled on purpose: the kernel is instruction-fetch bound, 8 unrolled copies of the blend cost more than the loop
-            for (int i = 0; i < 8; i++) w[i] = h.reduces ? h.paint_raw : src_over_x4(w[i], sfull, amask);
-          } else {
-#pragma unroll 1  // rolled on purpose: the kernel is instruction-fetch bound, 8 unrolled copies of the blend cost more than the loop
-            for (int i = 0; i < 8; i++) {
-              const uint32_t cov = (((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xffu;
-              if (cov == 0 || i < lo || i >= hi) continue;
-              n_cov++;
-              if (cov == full) w[i] = h.reduces ? h.paint_raw : src_over_x4(w[i], sfull, amask);
-              else w[i] = src_over_x4(w[i], st[cov], amask);
-            }
+          if (lo > 0 || hi < 8) {  // region / surface edge inside this lane's run of 8 pixels
+            uint32_t keep_e = 0u, keep_o = 0u;
+            for (int i = 0; i < 8; i++)
+              if (i >= lo && i < hi) ((i & 1) ? keep_o : keep_e) |= 0xffu << (8 * (i >> 1));
+            cov_e &= keep_e;
+            cov_o &= keep_o;
           }
-          reinterpret_cast<uint4*>(px)[lane] = v[0];
-          reinterpret_cast<uint4*>(px)[32 + lane] = v[1];
+        }
+        n_cov += nonzero_bytes(cov_e) + nonzero_bytes(cov_o);
+        if ((cov_e | cov_o) != 0u) {
+          uint4 v0 = reinterpret_cast<uint4*>(px)[lane], v1 = reinterpret_cast<uint4*>(px)[32 + lane];
+          blend_fast8(v0, v1, cov_e, cov_o, bt, tf.f.has_a ? 0x00ff00ffu : 0x000000ffu);
+          reinterpret_cast<uint4*>(px)[lane] = v0;
+          reinterpret_cast<uint4*>(px)[32 + lane] = v1;
         }
         __syncwarp();
         dirty = true;
