@@ -319,6 +319,143 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
   if (full1) m1 = ~0ull;
 }
 
+// ---- common case: at most 32 edges of the draw in this tile-row, so lane j holds the header of edge j.
+// Both per-row quantities the crossing pass needs come from ONE shared-memory difference array and one warp scan:
+//   .x  winding difference: +dir at the first row an edge LEFT of the tile is active on, -dir after its last row;
+//       the prefix sum is the backdrop winding of every row;
+//   .y  xor difference: bit j toggled at the first row and after the last row of CROSSING edge j; the prefix xor is,
+//       per row, the set of crossing edges active on it -- every lane then walks only the edges of its own rows.
+template <int W, bool TWO>
+Z2D_D void cross_pass32(const DevEdge* __restrict__ be, uint32_t my0, uint32_t my1, uint32_t up_b, int ys0, int sx0, int ncols, bool even_odd,
+                        int wl0, int wl1, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
+  uint64_t p0[W], p1[TWO ? W : 1];
+#pragma unroll
+  for (int k = 0; k < W; k++) {  // start from the backdrop winding (two's complement, bit-sliced)
+    p0[k] = (uint64_t)(int64_t)((int32_t)((uint32_t)wl0 << (31 - k)) >> 31);
+    if (TWO) p1[k] = (uint64_t)(int64_t)((int32_t)((uint32_t)wl1 << (31 - k)) >> 31);
+  }
+  for (uint32_t mine = my0 | (TWO ? my1 : 0u); mine; mine &= mine - 1) {
+    const int i = __ffs((int)mine) - 1;
+    const uint32_t bit = 1u << i;
+    const double4 ev = ld_edge(be + i);
+    const bool up = (up_b & bit) != 0u, a0 = (my0 & bit) != 0u, a1 = TWO && (my1 & bit) != 0u;
+    const double top = up ? ev.y : ev.x;
+    n_eval += (uint32_t)a0 + (uint32_t)a1;
+    if (a0) {
+      const int c0 = edge_col(ev, top, ys0, sx0, ncols);
+      if (c0 >= 0) {
+        const uint64_t mask = ~0ull << c0;
+        if (even_odd) p0[0] ^= mask; else wind_add<W>(p0, mask, up);
+      }
+    }
+    if (TWO && a1) {
+      const int c1 = edge_col(ev, top, ys0 + 1, sx0, ncols);
+      if (c1 >= 0) {
+        const uint64_t mask = ~0ull << c1;
+        if (even_odd) p1[0] ^= mask; else wind_add<TWO ? W : 1>(p1, mask, up);
+      }
+    }
+  }
+  uint64_t a = 0, b = 0;
+#pragma unroll
+  for (int k = 0; k < W; k++) {  // (even-odd is instantiated with W = 1: plane 0 is the parity)
+    a |= p0[k];
+    if (TWO) b |= p1[k];
+  }
+  m0 = a;
+  if (TWO) m1 = b;
+}
+
+template <bool TWO>
+Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, int sx0,
+                        uint32_t rule, uint2* __restrict__ diff, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
+  constexpr int ncols = TWO ? 64 : 16, nrows = TWO ? 64 : 16;
+  const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
+  const int lane = (int)(threadIdx.x & 31u);
+  const int sx_hi = sx0 + ncols;
+  reinterpret_cast<uint4*>(diff)[lane] = make_uint4(0u, 0u, 0u, 0u);  // entries 0 .. 65
+  if (lane == 0) reinterpret_cast<uint4*>(diff)[32] = make_uint4(0u, 0u, 0u, 0u);
+  bool cross = false, up = false;
+  __syncwarp();
+  if ((uint32_t)lane < n_be) {
+    const int4 h = __ldg(hd + lane);
+    const int r0 = max((h.z & 0x7fffffff) - ys_tile0, 0), r1 = min(h.w - ys_tile0, nrows - 1);
+    up = h.z < 0;
+    if (h.x <= sx_hi && r0 <= r1) {  // else entirely right of the tile, or not active on its rows
+      if (h.y < sx0) {               // entirely left: only its winding matters
+        const int dir = up ? 1 : -1;
+        atomicAdd(reinterpret_cast<int*>(&diff[r0].x), dir);
+        atomicAdd(reinterpret_cast<int*>(&diff[r1 + 1].x), -dir);
+      } else {
+        cross = true;
+        atomicXor(&diff[r0].y, 1u << lane);
+        atomicXor(&diff[r1 + 1].y, 1u << lane);
+      }
+    }
+  }
+  const uint32_t cross_b = __ballot_sync(0xffffffffu, cross), up_b = __ballot_sync(0xffffffffu, up);
+  __syncwarp();
+  int wl0, wl1 = 0;
+  uint32_t my0, my1 = 0u;
+  {
+    uint4 d4 = make_uint4(0u, 0u, 0u, 0u);  // {winding diff, xor diff} of rows 2 * lane, 2 * lane + 1 (16 rows: of row `lane`)
+    if (TWO) {
+      d4 = reinterpret_cast<const uint4*>(diff)[lane];
+    } else if (lane < 16) {
+      const uint2 d2 = diff[lane];
+      d4.x = d2.x;
+      d4.y = d2.y;
+    }
+    int incl = (int)d4.x + (int)d4.z;
+    uint32_t inclx = d4.y ^ d4.w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      const uint32_t tx = __shfl_up_sync(0xffffffffu, inclx, o);
+      if (lane >= o) {
+        incl += t;
+        inclx ^= tx;
+      }
+    }
+    if (TWO) {
+      wl0 = incl - (int)d4.z;
+      wl1 = incl;
+      my0 = inclx ^ d4.w;
+      my1 = inclx;
+    } else {
+      wl0 = __shfl_sync(0xffffffffu, incl, lane >> 1);
+      my0 = __shfl_sync(0xffffffffu, inclx, lane >> 1);
+    }
+  }
+  __syncwarp();  // diff is rewritten by the next call
+  if (cross_b == 0u) {
+    m0 = (even_odd ? (wl0 & 1) : (wl0 != 0)) ? ~0ull : 0ull;
+    m1 = (even_odd ? (wl1 & 1) : (wl1 != 0)) ? ~0ull : 0ull;
+    return;
+  }
+  if (even_odd) {
+    cross_pass32<1, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, true, wl0, wl1, m0, m1, n_eval);
+    return;
+  }
+  // the crossing edges of a row move its winding by at most their number: a backdrop beyond that keeps the whole row inside
+  const int k0 = __popc(my0), k1 = __popc(my1);
+  const bool full0 = abs(wl0) > k0, full1 = TWO && abs(wl1) > k1;
+  const int b0 = full0 ? 0 : wl0, b1 = full1 ? 0 : wl1;
+  const int bound = max(full0 ? 0 : abs(wl0) + k0, full1 ? 0 : abs(wl1) + k1);  // largest |winding| any of this lane's rows can reach
+  const int bmax = __reduce_max_sync(0xffffffffu, bound);
+  if (TWO && bmax <= 3) {
+    cross_pass32<3, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, false, b0, b1, m0, m1, n_eval);
+  } else if (bmax <= 15) {
+    cross_pass32<5, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, false, b0, b1, m0, m1, n_eval);
+  } else {  // (at most 32 crossing edges here: 8 planes hold +-64)
+    uint64_t dummy = 0;
+    cross_pass<8, false>(be, hd, n_be, (uint64_t)cross_b, ys0, sx0, ncols, false, b0, 0, m0, dummy, n_eval);
+    if (TWO) cross_pass<8, false>(be, hd, n_be, (uint64_t)cross_b, ys0 + 1, sx0, ncols, false, b1, 0, m1, dummy, n_eval);
+  }
+  if (full0) m0 = ~0ull;
+  if (full1) m1 = ~0ull;
+}
+
 // Draws flagged kDrawUnpaired only.  The reference pairs the sorted (filtered) crossings of a scanline and drops a
 // trailing unmatched one ("for (0..filtered_edge_set.len / 2)", multisample.zig:156 / supersample.zig / direct.zig), so
 // the inside run that would extend to +infinity is not drawn.  Which crossing that is depends on the order the
@@ -402,7 +539,7 @@ Z2D_D uint32_t nonzero_bytes(uint32_t x) { return (uint32_t)__popc(((x & 0x7f7f7
 __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(RasterArgs A) {
   __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
   __shared__ uint4 blend_tab[kRasterThreads / 32][17];
-  __shared__ int wdiff_s[kRasterThreads / 32][66];
+  __shared__ __align__(16) uint2 diff_s[kRasterThreads / 32][66];  // per warp: row difference array of tile_cover32 (int[132] view: tile_cover)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
   if (gt >= A.n_tiles) return;
@@ -476,7 +613,8 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         uint64_t m0 = 0, m1 = 0;
         const int sx0 = tx * kTile * Sc;
         if (Sc == 4) {
-          tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, wdiff_s[warp], m0, m1, n_eval);
+          if (nbe <= 32u) tile_cover32<true>(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, sx0, h.rule, diff_s[warp], m0, m1, n_eval);
+          else tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
           if (h.flags & kDrawUnpaired) {
             m0 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2, sx0, 64, m0);
             m1 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2 + 1, sx0, 64, m1);
@@ -489,7 +627,8 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
-          tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, wdiff_s[warp], m0, m1, n_eval);
+          if (nbe <= 32u) tile_cover32<false>(be, hd, nbe, ty * kTile, ty * kTile + row, sx0, h.rule, diff_s[warp], m0, m1, n_eval);
+          else tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
           if (h.flags & kDrawUnpaired) m0 = cut_open_tail(A, h, ty * kTile + row, sx0, 16, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
