@@ -514,7 +514,7 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
   const DevSurface s = sfcs[d.surface];
   d.valid = 0;
   draw_bands[i] = 0;
-  boxes[i] = DrawBox{-1, -1, -1, -1};
+  boxes[i] = DrawBox{-1, -1, -1, -1, 1, 0, 0u, 0u};
   if (d.n_edges == 0) return;
   const double top = f64_unorder(d.ext[0]), bottom = f64_unorder(d.ext[1]);
   const double left = f64_unorder(d.ext[2]), right = f64_unorder(d.ext[3]);
@@ -590,18 +590,28 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
     d.ty0 = d.ey0 - ty_org; d.ty1 = d.ey1 - ty_org;
   }
   d.valid = 1;
-  boxes[i] = DrawBox{d.tx0, d.tx1, d.ty0, d.ty1};
+  boxes[i] = DrawBox{d.tx0, d.tx1, d.ty0, d.ty1, d.ey0 - ty_org, d.ey1 - ty_org, 0u, 0u};
   draw_bands[i] = (uint32_t)(d.ey1 - d.ey0 + 1);
   if (counters && ry1 > ry0) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
 }
 
 // second half of the setup: (draw, tile-row) slot base + the compact record the raster kernel reads
 __global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off,
-                                   DrawHot* __restrict__ hots) {
+                                   DrawHot* __restrict__ hots, DrawBox* __restrict__ boxes, const DevSurface* __restrict__ sfcs) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
   DevDraw& d = draws[i];
   d.band_base = band_off[i];
+  {
+    const bool pre = d.unbounded && d.aa == Z2D_AA_MULTISAMPLE_4X, rowrec = d.mode == 2 && d.sim_rows > 0;
+    const bool unpaired = (d.flags & kDrawUnpaired) && d.sim_rows > 0;
+    const bool special = pre || rowrec || unpaired || d.aa == Z2D_AA_SUPERSAMPLE_4X;
+    const bool fast = !special && sfcs[d.surface].fmt <= Z2D_FMT_RGBA && d.src.kind == Z2D_PARAM_PIXEL && d.op == Z2D_OP_SRC_OVER &&
+                      (d.reduces || d.precision == Z2D_PRECISION_INTEGER);
+    boxes[i].band_base = d.band_base;
+    boxes[i].item_flags = (d.aa & kItemAaMask) | (d.rule == Z2D_FILL_EVEN_ODD ? kItemEvenOdd : 0u) | (special ? kItemSpecial : 0u) |
+                          (fast ? kItemFastBlend : 0u);
+  }
   DrawHot h;
   h.aa = d.aa; h.rule = d.rule; h.op = d.op; h.precision = d.precision;
   h.reduces = d.reduces; h.paint_raw = d.paint_raw; h.px_rgba = d.src.px_rgba; h.src_kind = d.src.kind;
@@ -647,7 +657,8 @@ __global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* _
 
 __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
                               const DevDraw* __restrict__ draws, const uint32_t* __restrict__ band_off,
-                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges, int4* __restrict__ band_hdr) {
+                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges, int4* __restrict__ band_hdr,
+                              uint2* __restrict__ band_xr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
   const DevDraw& d = draws[edge_draw[i]];
@@ -669,11 +680,19 @@ __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t*
   h.y = (int)fmax(fmin(ceil(xmax) + 1.0, big), -big);
   h.z = (int)fmin(ya, big) | (down ? 0 : (int)0x80000000);
   h.w = (int)fmax(yb, -1.0);
+  // tile columns this edge can touch (conservative, from the same bounds the raster kernel classifies with): the tile-row
+  // lists visit only [min, max] over the row's edges.  Stored as {0x7fffffff - min, max + 1} so that zero means "none".
+  const int S = (d.aa == Z2D_AA_NONE) ? 1 : 4;
+  const int span = kTile * S;
+  const uint32_t c_lo = 0x7fffffffu - (uint32_t)max(h.x - 1, 0) / (uint32_t)span;
+  const uint32_t c_hi = (uint32_t)max(h.y + 1, 0) / (uint32_t)span + 1u;
   for (int t = t0; t <= t1; t++) {
     const uint32_t b = d.band_base + (uint32_t)(t - d.ey0);
     const uint32_t slot = band_off[b] + atomicAdd(&band_cursor[b], 1u);
     band_edges[slot] = e;
     band_hdr[slot] = h;
+    atomicMax(&band_xr[b].x, c_lo);
+    atomicMax(&band_xr[b].y, c_hi);
   }
 }
 
@@ -785,7 +804,8 @@ Z2D_D uint32_t find_surface_by(const DevSurface* sfcs, uint32_t n_sfc, const uin
 template <bool WRITE>
 __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
                              const uint32_t* __restrict__ chunk_base, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
-                             const uint32_t* __restrict__ off, uint2* __restrict__ items) {
+                             const uint32_t* __restrict__ off, uint4* __restrict__ items, const uint32_t* __restrict__ band_off,
+                             const uint2* __restrict__ band_xr) {
   // one block per (surface, chunk of kDrawChunk draws); threads stride over the surface's tile-rows, so every thread of a
   // warp reads the SAME box at the same time (one broadcast transaction instead of 32 strided ones)
   const uint32_t si = find_surface_by(sfcs, n_sfc, chunk_base, blockIdx.x);
@@ -800,9 +820,32 @@ __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc
     uint32_t n = 0;
     const uint32_t o = WRITE ? off[w] : 0u;
     for (uint32_t i = b; i < e; i++) {
-      const int4 d = __ldg(reinterpret_cast<const int4*>(boxes) + i);  // {tx0, tx1, ty0, ty1}
+      const int4 d = __ldg(reinterpret_cast<const int4*>(boxes) + 2 * i);  // {tx0, tx1, ty0, ty1}
       if (d.x >= 0 && band >= d.z && band <= d.w) {
-        if (WRITE) items[o + n] = make_uint2(i, (uint32_t)d.x | ((uint32_t)d.y << 16));
+        if (WRITE) {
+          const int4 q = __ldg(reinterpret_cast<const int4*>(boxes) + 2 * i + 1);  // {es0, es1, band_base, item_flags}
+          uint32_t fl = (uint32_t)q.w, eb = 0u, nbe = 0u;
+          int tx0 = d.x, tx1 = d.y;
+          if (band >= q.x && band <= q.y) {
+            const uint32_t slot = (uint32_t)q.z + (uint32_t)(band - q.x);
+            eb = band_off[slot];
+            nbe = band_off[slot + 1] - eb;
+            fl |= kItemInRows;
+            if (!(fl & kItemSpecial)) {  // visit only the tile columns the edges of this row can touch
+              const uint2 xr = band_xr[slot];
+              tx0 = max(tx0, (int)(0x7fffffffu - xr.x));
+              tx1 = min(tx1, (int)xr.y - 1);
+            }
+          } else if (!(fl & kItemSpecial)) {
+            tx0 = 1;  // no edges on this tile row and nothing else to do there: never visited
+            tx1 = 0;
+          }
+          if (tx1 < tx0) {
+            tx0 = 0xffff;
+            tx1 = 0;
+          }
+          items[o + n] = make_uint4(i, (uint32_t)tx0 | ((uint32_t)tx1 << 16), eb, min(nbe, 0xffffffu) | (fl << 24));
+        }
         n++;
       }
     }
@@ -810,9 +853,9 @@ __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc
   }
 }
 template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, const uint32_t*, const DrawBox*, uint32_t*,
-                                             const uint32_t*, uint2*);
+                                             const uint32_t*, uint4*, const uint32_t*, const uint2*);
 template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const uint32_t*, const uint32_t*, const DrawBox*, uint32_t*,
-                                            const uint32_t*, uint2*);
+                                            const uint32_t*, uint4*, const uint32_t*, const uint2*);
 
 }  // namespace z2d
 #include "raster.cuh"
@@ -1034,23 +1077,25 @@ void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint
 void launch_expand_draws(const DrawIn* in, const StrokeIn* strokes, const DevSrc* srcs, DevDraw* draws, uint32_t n, cudaStream_t st) {
   if (n) k_expand_draws<<<(n + 127) / 128, 128, 0, st>>>(in, strokes, srcs, draws, n);
 }
-void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st) {
-  if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off, hots);
+void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, DrawBox* boxes, const DevSurface* sfcs,
+                             cudaStream_t st) {
+  if (n) k_assign_band_base<<<blocks_for(n, 256), 256, 0, st>>>(draws, n, band_off, hots, boxes, sfcs);
 }
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st) {
   if (n) k_bin_count<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_count);
 }
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
-                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st) {
-  if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges, band_hdr);
+                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, uint2* band_xr, cudaStream_t st) {
+  if (n) k_bin_scatter<<<blocks_for(n, 256), 256, 0, st>>>(edges, edge_draw, n, draws, band_off, band_cursor, band_edges, band_hdr, band_xr);
 }
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
-                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st) {
+                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint4* items, const uint32_t* band_off,
+                       const uint2* band_xr, cudaStream_t st) {
   if (!n_chunks) return;
   if (write)
-    k_band_lists<true><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
+    k_band_lists<true><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
   else
-    k_band_lists<false><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items);
+    k_band_lists<false><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
 }
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {

@@ -5,7 +5,7 @@
 namespace z2d {
 
 #ifndef Z2D_RASTER_THREADS
-#define Z2D_RASTER_THREADS 256
+#define Z2D_RASTER_THREADS 32
 #endif
 constexpr int kRasterThreads = Z2D_RASTER_THREADS;  // one warp per tile
 constexpr uint32_t kDrawChunk = 256; // draws per band-list work item
@@ -17,7 +17,7 @@ struct RasterArgs {
   uint32_t n_tiles;
   const uint32_t* work_base;   // per surface: first band-list work item
   const uint32_t* list_off;    // per work item (+1): offset into list_items
-  const uint2* list_items;     // (draw index, tx0 | tx1 << 16), draw order within a tile-row
+  const uint4* list_items;     // {draw, tx0 | tx1 << 16, first binned edge, edge count | kItem* << 24}, draw order within a tile-row
   const DevDraw* draws;
   const DrawHot* hots;
   const uint32_t* band_off;    // per (draw, tile-row) slot (+1): offset into band_edges
@@ -63,13 +63,15 @@ void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint3
                           uint32_t* curve_list /* n_nodes + 1 */, cudaStream_t st);
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st);
 void launch_expand_draws(const DrawIn* in, const StrokeIn* strokes, const DevSrc* srcs, DevDraw* draws, uint32_t n, cudaStream_t st);
-void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, cudaStream_t st);
+void launch_assign_band_base(DevDraw* draws, uint32_t n, const uint32_t* band_off, DrawHot* hots, DrawBox* boxes, const DevSurface* sfcs,
+                             cudaStream_t st);
 void launch_bin_count(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, uint32_t* band_count, cudaStream_t st);
 void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_t n, const DevDraw* draws, const uint32_t* band_off,
-                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, cudaStream_t st);
+                        uint32_t* band_cursor, DevEdge* band_edges, int4* band_hdr, uint2* band_xr /* zeroed, one per slot */, cudaStream_t st);
 // chunk_base[s] = number of (surface, kDrawChunk-draw chunk) blocks before surface s; one block per chunk
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
-                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint2* items, cudaStream_t st);
+                       uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint4* items, const uint32_t* band_off,
+                       const uint2* band_xr, cudaStream_t st);
 // exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);

@@ -325,8 +325,14 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
 //       the prefix sum is the backdrop winding of every row;
 //   .y  xor difference: bit j toggled at the first row and after the last row of CROSSING edge j; the prefix xor is,
 //       per row, the set of crossing edges active on it -- every lane then walks only the edges of its own rows.
+Z2D_D double4 lds_edge(const uint4* __restrict__ es, int i) {  // edge i of the pair from shared memory ({y0, y1} | {x_start, x_inc})
+  const uint4 a = es[i], b = es[32 + i];
+  return make_double4(__hiloint2double((int)a.y, (int)a.x), __hiloint2double((int)a.w, (int)a.z), __hiloint2double((int)b.y, (int)b.x),
+                      __hiloint2double((int)b.w, (int)b.z));
+}
+
 template <int W, bool TWO>
-Z2D_D void cross_pass32(const DevEdge* __restrict__ be, uint32_t my0, uint32_t my1, uint32_t up_b, int ys0, int sx0, int ncols, bool even_odd,
+Z2D_D void cross_pass32(const uint4* __restrict__ es, uint32_t my0, uint32_t my1, uint32_t up_b, int ys0, int sx0, int ncols, bool even_odd,
                         int wl0, int wl1, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
   uint64_t p0[W], p1[TWO ? W : 1];
 #pragma unroll
@@ -337,7 +343,7 @@ Z2D_D void cross_pass32(const DevEdge* __restrict__ be, uint32_t my0, uint32_t m
   for (uint32_t mine = my0 | (TWO ? my1 : 0u); mine; mine &= mine - 1) {
     const int i = __ffs((int)mine) - 1;
     const uint32_t bit = 1u << i;
-    const double4 ev = ld_edge(be + i);
+    const double4 ev = lds_edge(es, i);
     const bool up = (up_b & bit) != 0u, a0 = (my0 & bit) != 0u, a1 = TWO && (my1 & bit) != 0u;
     const double top = up ? ev.y : ev.x;
     n_eval += (uint32_t)a0 + (uint32_t)a1;
@@ -368,7 +374,7 @@ Z2D_D void cross_pass32(const DevEdge* __restrict__ be, uint32_t my0, uint32_t m
 
 template <bool TWO>
 Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, int sx0,
-                        uint32_t rule, uint2* __restrict__ diff, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
+                        uint32_t rule, uint2* __restrict__ diff, uint4* __restrict__ es, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
   constexpr int ncols = TWO ? 64 : 16, nrows = TWO ? 64 : 16;
   const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
   const int lane = (int)(threadIdx.x & 31u);
@@ -379,6 +385,12 @@ Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__
   __syncwarp();
   if ((uint32_t)lane < n_be) {
     const int4 h = __ldg(hd + lane);
+    {  // the edge itself goes to shared memory now (coalesced, independent of the header): the crossing pass gathers from there
+      const uint4* g = reinterpret_cast<const uint4*>(be + lane);
+      const uint4 e0 = __ldg(g), e1 = __ldg(g + 1);
+      es[lane] = e0;
+      es[32 + lane] = e1;
+    }
     const int r0 = max((h.z & 0x7fffffff) - ys_tile0, 0), r1 = min(h.w - ys_tile0, nrows - 1);
     up = h.z < 0;
     if (h.x <= sx_hi && r0 <= r1) {  // else entirely right of the tile, or not active on its rows
@@ -434,7 +446,7 @@ Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__
     return;
   }
   if (even_odd) {
-    cross_pass32<1, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, true, wl0, wl1, m0, m1, n_eval);
+    cross_pass32<1, TWO>(es, my0, my1, up_b, ys0, sx0, ncols, true, wl0, wl1, m0, m1, n_eval);
     return;
   }
   // the crossing edges of a row move its winding by at most their number: a backdrop beyond that keeps the whole row inside
@@ -444,9 +456,11 @@ Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__
   const int bound = max(full0 ? 0 : abs(wl0) + k0, full1 ? 0 : abs(wl1) + k1);  // largest |winding| any of this lane's rows can reach
   const int bmax = __reduce_max_sync(0xffffffffu, bound);
   if (TWO && bmax <= 3) {
-    cross_pass32<3, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, false, b0, b1, m0, m1, n_eval);
-  } else if (bmax <= 15) {
-    cross_pass32<5, TWO>(be, my0, my1, up_b, ys0, sx0, ncols, false, b0, b1, m0, m1, n_eval);
+    cross_pass32<3, TWO>(es, my0, my1, up_b, ys0, sx0, ncols, false, b0, b1, m0, m1, n_eval);
+  } else if (bmax <= 15) {  // one row at a time: 5 planes x 2 rows would not fit the register budget of the kernel
+    uint64_t dummy = 0;
+    cross_pass32<5, false>(es, my0, 0u, up_b, ys0, sx0, ncols, false, b0, 0, m0, dummy, n_eval);
+    if (TWO) cross_pass32<5, false>(es, my1, 0u, up_b, ys0 + 1, sx0, ncols, false, b1, 0, m1, dummy, n_eval);
   } else {  // (at most 32 crossing edges here: 8 planes hold +-64)
     uint64_t dummy = 0;
     cross_pass<8, false>(be, hd, n_be, (uint64_t)cross_b, ys0, sx0, ncols, false, b0, 0, m0, dummy, n_eval);
@@ -533,14 +547,18 @@ Z2D_D void blend_fast8(uint4& v0, uint4& v1, uint32_t cov_e, uint32_t cov_o, con
 }
 Z2D_D uint32_t nonzero_bytes(uint32_t x) { return (uint32_t)__popc(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu | x) & 0x80808080u); }
 
+// One warp per tile.  The default is ONE WARP PER CTA (32 threads, 32 CTAs per SM at 64 registers): everything derived from
+// blockIdx is then uniform for the compiler (uniform registers and datapath instead of one copy per lane), which measured
+// 3.03 ms against 3.34 ms (128 threads) and 3.9 ms (256 threads) on the 100 k-path scene.
 #ifndef Z2D_RASTER_MIN_CTAS
-#define Z2D_RASTER_MIN_CTAS 4
+#define Z2D_RASTER_MIN_CTAS (2048 / Z2D_RASTER_THREADS > 32 ? 32 : 2048 / Z2D_RASTER_THREADS)
 #endif
 __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(RasterArgs A) {
   __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
   __shared__ uint4 blend_tab[kRasterThreads / 32][17];
   __shared__ __align__(16) uint2 diff_s[kRasterThreads / 32][66];  // per warp: row difference array of tile_cover32 (int[132] view: tile_cover)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(16) uint4 edge_s[kRasterThreads / 32][2][32];  // per warp: the (<= 32) binned edges of the current pair
+  const int warp = kRasterThreads == 32 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
   if (gt >= A.n_tiles) return;
   // tile -> surface, tx, ty
@@ -580,42 +598,48 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
   const bool vec_ok = tf.is32 && row_ok && px0 + 8 <= S.w && ((row_idx + (size_t)px0) & 3) == 0;  // 2 x 128-bit global access
 
   for (uint32_t base = lb; base < le; base += 32) {
-    uint2 it = make_uint2(0, 0);
+    uint4 it = make_uint4(0u, 0u, 0u, 0u);
     bool hit = false;
     if (base + lane < le) {
-      it = A.list_items[base + lane];
+      it = __ldg(A.list_items + base + lane);
       const int itx0 = (int)(it.y & 0xffffu), itx1 = (int)(it.y >> 16);
       hit = tx >= itx0 && tx <= itx1;
     }
     uint32_t hits = __ballot_sync(0xffffffffu, hit);
+    n_pairs += (uint32_t)__popc(hits);
     while (hits) {
       const int src_lane = __ffs(hits) - 1;
       hits &= hits - 1;
       const uint32_t di = __shfl_sync(0xffffffffu, it.x, src_lane);
-      const DrawHot& h = A.hots[di];  // read on demand (uniform, L1-resident): keeping all 24 fields live costs more in spills
+      const uint32_t iw = __shfl_sync(0xffffffffu, it.w, src_lane);
+      const uint32_t ifl = iw >> 24;
+      const DrawHot& h = A.hots[di];  // read on demand (uniform): region, source pixel; the list item carries the rest
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&h));
 
       // ---- coverage
-      const int aa = (int)h.aa;
-      const int Sc = (aa == Z2D_AA_NONE) ? 1 : 4;
+      const int aa = (int)(ifl & kItemAaMask);
+      const uint32_t rule = (ifl & kItemEvenOdd) ? (uint32_t)Z2D_FILL_EVEN_ODD : (uint32_t)Z2D_FILL_NON_ZERO;
+      const bool special = (ifl & kItemSpecial) != 0u;
       uint32_t cov_e = 0, cov_o = 0;  // per-pixel coverage bytes: even pixels in cov_e, odd in cov_o
-      const bool in_rows = ty >= h.ey0 && ty <= h.ey1;
-      const bool pre = h.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
+      const bool in_rows = (ifl & kItemInRows) != 0u;
+      const bool pre = special && h.unbounded && aa == Z2D_AA_MULTISAMPLE_4X;
       const bool all_px = aa == Z2D_AA_SUPERSAMPLE_4X;  // every pixel of the region is composited, even at coverage 0
-      const bool rowrec = (h.flags & kDrawRowRecords) != 0u;
-      if (!in_rows && !pre && !rowrec) continue;
-      n_pairs++;
+      const bool rowrec = special && (h.flags & kDrawRowRecords) != 0u;
       if (in_rows) {
-        const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
-        const uint32_t eb = A.band_off[bslot], ee = A.band_off[bslot + 1];
+        uint32_t eb = __shfl_sync(0xffffffffu, it.z, src_lane), nbe = iw & 0xffffffu;
+        if (nbe == 0xffffffu) {  // (count does not fit the item)
+          const uint32_t bslot = h.band_base + (uint32_t)(ty - h.ey0);
+          nbe = A.band_off[bslot + 1] - eb;
+        }
         const DevEdge* be = A.band_edges + eb;
         const int4* hd = A.band_hdr + eb;
-        const uint32_t nbe = ee - eb;
+        const bool unpaired = special && (h.flags & kDrawUnpaired) != 0u;
         uint64_t m0 = 0, m1 = 0;
-        const int sx0 = tx * kTile * Sc;
-        if (Sc == 4) {
-          if (nbe <= 32u) tile_cover32<true>(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, sx0, h.rule, diff_s[warp], m0, m1, n_eval);
-          else tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, h.rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
-          if (h.flags & kDrawUnpaired) {
+        if (aa != Z2D_AA_NONE) {
+          const int sx0 = tx * kTile * 4;
+          if (nbe <= 32u) tile_cover32<true>(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, sx0, rule, diff_s[warp], edge_s[warp][0], m0, m1, n_eval);
+          else tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
+          if (unpaired) {
             m0 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2, sx0, 64, m0);
             m1 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2 + 1, sx0, 64, m1);
           }
@@ -627,9 +651,10 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           cov_e = (a & 0x0f0f0f0fu) + (b & 0x0f0f0f0fu) + (c & 0x0f0f0f0fu) + (e2 & 0x0f0f0f0fu);
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
-          if (nbe <= 32u) tile_cover32<false>(be, hd, nbe, ty * kTile, ty * kTile + row, sx0, h.rule, diff_s[warp], m0, m1, n_eval);
-          else tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, h.rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
-          if (h.flags & kDrawUnpaired) m0 = cut_open_tail(A, h, ty * kTile + row, sx0, 16, m0);
+          const int sx0 = tx * kTile;
+          if (nbe <= 32u) tile_cover32<false>(be, hd, nbe, ty * kTile, ty * kTile + row, sx0, rule, diff_s[warp], edge_s[warp][0], m0, m1, n_eval);
+          else tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
+          if (unpaired) m0 = cut_open_tail(A, h, ty * kTile + row, sx0, 16, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
             cov_e |= ((bits >> i) & 1u) << (4 * i);  // byte i/2
@@ -683,8 +708,7 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         dirty = true;
         continue;
       }
-      if (tf.is32 && h.src_kind == Z2D_PARAM_PIXEL && h.op == Z2D_OP_SRC_OVER && !pre && !all_px &&
-          (h.reduces || h.precision == Z2D_PRECISION_INTEGER)) {
+      if (ifl & kItemFastBlend) {
         // fast path: single-pixel source, integer src_over.  Lanes 1..16 build the source at each coverage level
         // (multisample.zig:223: alpha 16 * cov - 1; full coverage: unmasked) in blend-ready form, then every lane blends
         // its 8 pixels straight-line (no divergence between fully and partially covered pixels, no register indexing).

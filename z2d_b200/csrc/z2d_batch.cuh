@@ -121,8 +121,22 @@ struct DevEdge {
 // tile box, the raster kernel only the fields below (the 300-byte DevDraw is touched
 // again only for gradient / dither sources).
 struct DrawBox {  // tx0 < 0 => draw not valid
-  int32_t tx0, tx1, ty0, ty1;
+  int32_t tx0, tx1, ty0, ty1;   // tile box of this surface the draw touches (inclusive)
+  int32_t es0, es1;             // tile rows of this surface that hold binned edges (inclusive; empty: es0 > es1)
+  uint32_t band_base;           // first (draw, tile-row) slot: slot of surface tile row t = band_base + (t - es0)
+  uint32_t item_flags;          // kItem* bits every list item of the draw carries (k_assign_band_base)
 };
+
+// One entry of a tile-row's ordered draw list (k_band_lists -> k_raster_tiles), everything the raster kernel needs to start
+// on the pair without touching another table:
+//   .x draw index   .y first | last << 16 tile column to visit (the x-range of the edges binned to THIS tile row, not the
+//   draw's whole box: tiles left or right of every edge of a closed shape see winding 0)   .z first binned edge
+//   .w number of binned edges (24 bits; 0xffffff: look it up) | flags << 24
+constexpr uint32_t kItemAaMask = 3u;       // Z2D_AA_* of the draw
+constexpr uint32_t kItemEvenOdd = 4u;
+constexpr uint32_t kItemInRows = 8u;       // this tile row holds binned edges of the draw
+constexpr uint32_t kItemSpecial = 16u;     // unbounded pre-clear / row records / supersample / dangling edge: consult DrawHot
+constexpr uint32_t kItemFastBlend = 32u;   // 32-bit surface, single-pixel source, integer src_over: table-driven blend
 struct alignas(16) DrawHot {
   uint32_t aa, rule, op, precision;
   uint32_t reduces, paint_raw, px_rgba, src_kind;

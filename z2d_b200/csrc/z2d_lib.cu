@@ -179,7 +179,7 @@ struct z2d_ctx {
   DevBuf d_band_edges, d_list_cnt, d_list_off, d_list_items, d_scan_tmp;
   DevBuf d_comp_grads, d_comp_stop_off, d_comp_stop_col;
   uint32_t* h_total = nullptr;  // pinned readback slot
-  DevBuf d_counters, d_boxes, d_hots, d_band_hdr;
+  DevBuf d_counters, d_boxes, d_hots, d_band_hdr, d_band_xr;
   DevBuf d_export, d_gamma;  // z2d_surface_export: scanline staging, sRGB channel table
   DevBuf d_sim_rows, d_sim_perm, d_sim_x;  // k_edge_sim: row records, per-edge scratch
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -554,7 +554,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
   CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
   launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
-                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, st);
+                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
   CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + n_cnt, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
@@ -568,7 +568,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   // K1 (emit half)
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
-  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint2) + 16));
+  CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint4) + 16));
+  CK(c, c->d_band_xr.ensure((size_t)n_slots * sizeof(uint2) + 16));
   CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
   CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
   launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
@@ -590,9 +591,11 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, cudaEventRecord(c->ev[1], st));
 
   // K3a: edges -> (draw, tile-row) lists
-  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), st);
+  launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), c->d_boxes.as<DrawBox>(),
+                          S.sfcs, st);
   CK(c, cudaMemsetAsync(c->d_band_count.p, 0, (size_t)n_slots * 4 + 16, st));
   CK(c, cudaMemsetAsync(c->d_band_cursor.p, 0, (size_t)n_slots * 4 + 16, st));
+  CK(c, cudaMemsetAsync(c->d_band_xr.p, 0, (size_t)n_slots * sizeof(uint2) + 16, st));
   launch_bin_count(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_count.as<uint32_t>(), st);
   CK(c, scan(c->d_band_count, c->d_band_off, n_slots));
   uint32_t n_band_edges = 0;
@@ -603,12 +606,13 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, c->d_band_edges.ensure((size_t)n_band_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_band_hdr.ensure((size_t)n_band_edges * sizeof(int4) + 32));
   launch_bin_scatter(c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), n_edges, c->d_draws.as<DevDraw>(), c->d_band_off.as<uint32_t>(),
-                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), c->d_band_hdr.as<int4>(), st);
+                     c->d_band_cursor.as<uint32_t>(), c->d_band_edges.as<DevEdge>(), c->d_band_hdr.as<int4>(), c->d_band_xr.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[2], st));
 
   // K3b (write half): ordered draw list per surface tile-row
   launch_band_lists(true, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
-                    c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint2>(), st);
+                    c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint4>(), c->d_band_off.as<uint32_t>(),
+                    c->d_band_xr.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
   // K4: fused coverage + compositing
@@ -618,7 +622,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.n_tiles = m.n_tiles;
   A.work_base = S.work_base;
   A.list_off = c->d_list_off.as<uint32_t>();
-  A.list_items = c->d_list_items.as<uint2>();
+  A.list_items = c->d_list_items.as<uint4>();
   A.draws = c->d_draws.as<DevDraw>();
   A.hots = c->d_hots.as<DrawHot>();
   A.band_off = c->d_band_off.as<uint32_t>();
@@ -1073,6 +1077,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   c->d_counters.release();
   c->d_boxes.release();
   c->d_band_hdr.release();
+  c->d_band_xr.release();
   c->d_hots.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
