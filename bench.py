@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""Benchmark of the fill -> coverage -> composite hot path (BASELINE.json config 2).
+"""Benchmark of the fill -> coverage -> composite hot path (BASELINE.json config 2; the other configs behind --workload).
 
   python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA library)
   python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (rank 0 only)
+  python bench.py --workload c3|c4|c5 ...                  # config 3 (strokes) / config 4 (compositor sweep) / config 5 (scene batch)
 
 A *step* is one pass of the hot path over one batch: a zeroed 4096x4096 RGBA8
 canvas receives 100 000 ordered `painter.fill` calls (random closed 4-cubic
@@ -139,53 +140,77 @@ def oracle_lib(fast=True):
     return load_oracle(fast=fast)
 
 
-def time_oracle(scene, n_sample, lib):
-    """Render the first n_sample draws of the scene with the CPU restatement; returns (seconds, covered_px)."""
-    from z2d_b200 import abi
-    buf = np.zeros(scene.width * scene.height * 4, dtype=np.uint8)
-    cmds = scene.draw_cmds(0, 0, n_sample)
+def zig_probe():
+    """BASELINE.md section 3, tier A: is there a Zig toolchain on this box that could build the reference itself?"""
+    import shutil
+    exe = shutil.which("zig")
+    if not exe:
+        return "zig: not found on PATH (reference cannot be built; CPU arm = C++ restatement, oracle/)"
+    try:
+        return "zig " + subprocess.run([exe, "version"], capture_output=True, text=True, timeout=10).stdout.strip() + \
+               " found, but /root/reference is not shipped to the GPU box: CPU arm = C++ restatement (oracle/)"
+    except Exception as e:  # noqa: BLE001
+        return f"zig probe failed: {e}"
+
+
+def canvas_scene(args, rank):
+    """The ordered single-canvas workloads: config 2 (fills) and config 3 (strokes)."""
+    from z2d_b200 import sharding, workloads
+    if args.workload == "c3":
+        scene = workloads.stroke_paths_scene(args.strokes, 2048, seed=sharding.scene_seed(0x7A326403, rank))
+        desc = (f"BASELINE config 3 per GPU: 2048x2048 RGBA8, {args.strokes} open sub-paths (polylines of 5-12 vertices / two-segment cubic "
+                "Beziers), widths 1.5-12, round / miter(10) joins, round caps, every 2nd path dashed [3w, 2w], translucent src_over, default AA")
+    else:
+        scene = workloads.cubic_paths_scene(args.paths, args.size, seed=sharding.scene_seed(sharding.BASE_SEED_C2, rank))
+        desc = (f"BASELINE config 2 per GPU: {args.size}x{args.size} RGBA8, {args.paths} random closed 4-cubic paths, "
+                "non-zero/even-odd alternating, translucent src_over, default AA (MSAA 4x4), ordered")
+    return scene, desc
+
+
+def time_oracle(scene, lo, hi, lib):
+    """Render draws [lo, hi) of the scene with the CPU restatement; returns (seconds, covered_px, surface bytes)."""
+    from tests.oracle_backend import render_scene
     lib.z2d_ref_covered_px(1)
-    P = C.POINTER
-    fill = lib.z2d_ref_fill
-    ptr = buf.ctypes.data_as(C.c_void_p)
-    pat = C.cast(C.c_void_p(int(cmds["pattern"][0])), P(abi.PatternPOD))
     t0 = time.perf_counter()
-    for i in range(n_sample):
-        rc = fill(ptr, 3, scene.width, scene.height, C.cast(C.c_void_p(int(cmds["pattern"][i])), P(abi.PatternPOD)),
-                  C.cast(C.c_void_p(int(cmds["nodes"][i])), P(abi.Node)), int(cmds["n_nodes"][i]),
-                  C.cast(C.c_void_p(int(cmds["fill"][i])), P(abi.FillOptsPOD)))
-        assert rc == 0
+    buf = render_scene(lib, scene, lo, hi)
     dt = time.perf_counter() - t0
-    del pat
     return dt, int(lib.z2d_ref_covered_px(1)), buf
+
+
+CPU_NOTE = ("C++ restatement of z2d's CPU path (oracle/, g++ -O3 -march=native -ffp-contract=off), not z2d itself; it composites span "
+            "pixels one by one where z2d memsets opaque spans, so it is a lower bound on z2d's own speed; z2d is single threaded")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from z2d_b200 import workloads
-    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=0x7A326402)
+    if args.workload == "c5":
+        import bench_extra
+        return bench_extra.reference_c5(args)
+    scene, desc = canvas_scene(args, 0)
     lib = oracle_lib(fast=True)
-    n_sample = min(args.ref_sample, scene.n)
-    for _ in range(args.warmup):
-        time_oracle(scene, min(200, n_sample), lib)
-    tot_t, tot_px = 0.0, 0
-    for _ in range(args.steps):
-        dt, px, _ = time_oracle(scene, n_sample, lib)
+    for _ in range(min(args.warmup, 2)):
+        time_oracle(scene, 0, min(500, scene.n), lib)
+    # every step renders the WHOLE scene (same config as the GPU arm); the number of steps is cut so that the run stays within
+    # a couple of minutes (one pass over the 100 k-path scene takes ~20 s on one core)
+    dt, px, _ = time_oracle(scene, 0, scene.n, lib)
+    steps = max(1, min(args.steps, int(args.ref_budget_s / max(dt, 1e-3))))
+    tot_t, tot_px = dt, px
+    for _ in range(steps - 1):
+        dt, px, _ = time_oracle(scene, 0, scene.n, lib)
         tot_t += dt
         tot_px += px
     mpix = tot_px / tot_t / 1e6
-    paths_s = n_sample * args.steps / tot_t
+    paths_s = scene.n * steps / tot_t
     line = {
-        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "paths_per_s": paths_s,
-        "config": {"workload": f"BASELINE config 2: {args.size}x{args.size} RGBA8, {args.paths} random closed 4-cubic paths, "
-                               "non-zero/even-odd alternating, translucent src_over, default AA (MSAA 4x4), ordered",
-                   "sample": f"first {n_sample} draws of the scene per step"},
-        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": paths_s,
-                         "sample": f"first {n_sample} of {scene.n} draws per step, x{args.steps} steps; C++ restatement of z2d's CPU path "
-                                   "(oracle/, g++ -O3 -march=native -ffp-contract=off), not z2d itself (no Zig toolchain); z2d is single threaded"},
+        "config": {"workload": desc, "sample": f"the whole scene ({scene.n} draws) per step; {steps} step(s) of the {args.steps} requested "
+                                              f"fit the {args.ref_budget_s:.0f} s budget"},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": paths_s, "zig": zig_probe(),
+                         "sample": f"whole scene, {scene.n} draws per step, x{steps} steps, {tot_t:.1f} s; " + CPU_NOTE +
+                                   f"; host has {os.cpu_count()} cores, the ordered canvas uses 1"},
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -194,7 +219,8 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from z2d_b200 import abi, sharding, workloads
+    import bench_extra
+    from z2d_b200 import abi, sharding
     from z2d_b200.cuda_backend import CudaBackend
     from z2d_b200.host import Pixel, Surface
 
@@ -204,23 +230,58 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     cb = CudaBackend(local_rank, stream=stream.cuda_stream)
+    lib = cb.lib
+    ddist = dist if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "c4":
+        if rank == 0:
+            peak, kind = peaks()
+            cells = bench_extra.run_c4(cb, peak, full=not args.quick)
+            head = [c for c in cells if c["format"] == "rgba" and c["source"] == "pixel" and c["op"] == "src_over" and c["precision"] == "integer"][0]
+            rect = bench_extra.run_c4_fill(cb, peak)
+            line = {"metric": "composited GB/s (algorithmic bytes)", "value": head["gbs"], "unit": "GB/s", "n_gpus": 1, "steps": 3, "warmup": 1,
+                    "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                    "config": {"workload": "BASELINE config 4: 8192x8192, {rgba,rgb,alpha8,alpha4,alpha2,alpha1} x {pixel,linear,radial,conic,+sRGB,+HSL} x "
+                                           "dither {none,bayer,blue_noise} x operators x {integer,float}; one SurfaceCompositor.run per cell; value = the "
+                                           "RGBA8 src_over single-pixel cell", "l2": "256 MiB surfaces for the 32-bit formats exceed L2; packed formats do not (8-64 MiB)"},
+                    "roofline": {"kernel": "k_composite_fast", "bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                                 "peak_kind": kind, "traffic": ncu_traffic("composite")[0]},
+                    "c4_summary": bench_extra.c4_summary(cells), "c4_context_fill": rect, "c4_cells": cells, "gpu_launches": len(cells) * 4}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    if args.workload == "c5":
+        c5 = bench_extra.run_c5(cb, rank, world, ddist, args.scenes, 1024, max(1, min(args.steps, 5)), 1, with_cpu=not args.no_cpu_baseline)
+        if rank == 0:
+            line = {"metric": METRIC, "value": c5["mpix_s"], "unit": UNIT, "n_gpus": world, "steps": c5["steps"], "warmup": c5["warmup"],
+                    "ms_per_step": c5["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                    "data": "synthetic", "scenes_per_s": c5["scenes_per_s"], "config": {"workload": c5["workload"], "parallelism": c5["parallelism"]},
+                    "e2e": c5["e2e"], "gpu_launches": c5["gpu_launches"], "cpu_baseline": c5.get("cpu_baseline"), "c5": c5}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     if args.chunk >= 0:
         cb.set_chunk(args.chunk)
-    lib = cb.lib
-
-    scene = workloads.cubic_paths_scene(args.paths, args.size, seed=sharding.scene_seed(sharding.BASE_SEED_C2, rank))
-    sfc = Surface(abi.Format.rgba, args.size, args.size, None, cb)
+    scene, desc = canvas_scene(args, rank)
+    W, H = scene.width, scene.height
+    sfc = Surface(abi.Format.rgba, W, H, None, cb)
     cmds = scene.draw_cmds(sfc.handle)
     cmds_p = cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD))
     zero = Pixel.rgba(0, 0, 0, 0)
     nbytes = sfc.byte_len()
     host_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     host_ptr = C.c_void_p(host_out.data_ptr())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def e2e_step():
         sfc.paint_pixel(zero)
@@ -234,7 +295,6 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e (host buffers, H2D + D2H inside the timed region)
     for _ in range(max(args.warmup, 3)):
         e2e_step()
-    st = cb.stats()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -281,9 +341,10 @@ def run_ours(args, rank, world, local_rank):
         raster_ms.append(s["ms_raster"])
         total_ms.append(s["ms_total"])
     st = cb.stats()
+    cb.set_chunk(32768)
 
     (dev_ms, e2e_ms), (covered_all, draws_all) = sharding.reduce_timing(
-        [dev_ms, e2e_s * 1e3], [st["covered_px"], st["draws"]], device="cuda", dist=dist if world > 1 else None)
+        [dev_ms, e2e_s * 1e3], [st["covered_px"], st["draws"]], device="cuda", dist=ddist)
 
     # ---- compositor kernel roofline (config 4 shape: 8192^2 RGBA8 src_over, single-pixel source)
     comp = None
@@ -295,16 +356,21 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         olib = oracle_lib(fast=True)
         n_sample = min(args.cpu_sample, scene.n)
-        dt, px, ref_buf = time_oracle(scene, n_sample, olib)
-        cpu = {"value": px / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": n_sample / dt,
-               "sample": f"first {n_sample} of {scene.n} draws, {dt:.1f} s; C++ restatement of z2d's CPU path (oracle/, -O3 -march=native), "
-                         f"1 thread (z2d is single threaded); host has {os.cpu_count()} cores"}
+        dt, px, ref_buf = time_oracle(scene, 0, n_sample, olib)
+        cpu = {"value": px / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "paths_per_s": n_sample / dt, "zig": zig_probe(),
+               "sample": f"first {n_sample} of {scene.n} draws, {dt:.1f} s; " + CPU_NOTE + f"; host has {os.cpu_count()} cores"}
         # parity spot check of the same sample on the device
-        chk = Surface(abi.Format.rgba, args.size, args.size, None, cb)
+        chk = Surface(abi.Format.rgba, W, H, None, cb)
         c2 = scene.draw_cmds(chk.handle, 0, n_sample)
         cb.submit(c2.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), n_sample)
         cpu["parity_sample_equal"] = bool(np.array_equal(chk.download(), ref_buf))
         chk.deinit()
+    sfc.deinit()
+
+    # ---- config 5 (the configuration that shards): batch of 1024^2 mixed scenes, scene s -> rank s mod N, strong scaling
+    c5 = None
+    if not args.no_c5:
+        c5 = bench_extra.run_c5(cb, rank, world, ddist, args.scenes, 1024, 2, 1, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
     if rank == 0:
         peak, peak_kind = peaks()
@@ -318,10 +384,12 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "paths_per_s": draws_all * steps / (dev_ms * 1e-3),
-            "config": {"workload": f"BASELINE config 2 per GPU: {args.size}x{args.size} RGBA8, {args.paths} random closed 4-cubic paths, "
-                                   "non-zero/even-odd alternating, translucent src_over, default AA (MSAA 4x4), ordered",
-                       "parallelism": f"independent scenes, 1 per GPU x{world} (no data-path collective)",
-                       "l2": "per-step inputs (nodes+draw table+edges+canvas ~ 340 MB) exceed the 126 MB L2; canvas cleared every step"},
+            "config": {"workload": desc,
+                       "parallelism": f"independent scenes, 1 per GPU x{world} (no data-path collective); the sharded configuration (config 5, "
+                                      "scene s -> rank s mod N, strong scaling) is the `c5` block of this line",
+                       "value_definition": "inputs (nodes, draw records) resident in HBM when the timed region starts (z2d_replay); the node upload "
+                                           "and the surface read-back are inside `e2e`",
+                       "l2": "per-step inputs (nodes+draw table+edges+canvas) exceed the 126 MB L2; canvas cleared every step"},
             "e2e": {"value": e2e_mpix, "unit": UNIT, "ms_per_step": e2e_ms / steps, "paths_per_s": draws_all * steps / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nbytes), "breakdown": e2e_breakdown},
             "gpu_launches": int((st["kernel_launches"] + 1) * steps),
@@ -331,7 +399,8 @@ def run_ours(args, rank, world, local_rank):
                          "peak_kind": peak_kind, "ms": r_ms,
                          "algorithmic_bytes": algo_bytes,
                          "note": "algorithmic = 8 B per composited pixel (read+write RGBA8 per path, SURVEY 8d) + 32 B per binned edge; "
-                                 "the tile-resident design touches each canvas tile once per batch, so DRAM traffic is far below this"},
+                                 "the tile-resident design touches each canvas tile once per batch, so DRAM traffic is far below this: "
+                                 "the kernel is instruction bound, see raster_throughput and profiles/"},
             "stages_ms": {"flatten": st["ms_flatten"], "bin": st["ms_bin"], "lists": st["ms_lists"], "raster": r_ms,
                           "pipeline_total": float(np.mean(total_ms))},
             "counters": {k: int(st[k]) for k in ("draws", "nodes", "edges", "band_edges", "tile_items", "tiles", "covered_px", "region_px",
@@ -343,6 +412,7 @@ def run_ours(args, rank, world, local_rank):
                                   "composited_px_per_s": st["covered_px"] / (r_ms * 1e-3)},
             "roofline_composite": comp,
             "cpu_baseline": cpu,
+            "c5": c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -375,7 +445,8 @@ def composite_roofline(cb, args):
     return {"kernel": "k_composite_fast<integer, pixel source>", "workload": "8192x8192 RGBA8 src_over, single-pixel source (BASELINE config 4 shape)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "ms": ms,
             "mpix_per_s": n * n / (ms * 1e-3) / 1e6, "peak_kind": kind, "traffic": ncu_traffic("composite")[0],
-            "traffic_source": ncu_traffic("composite")[1], "algorithmic_bytes": 8.0 * n * n}
+            "traffic_source": ncu_traffic("composite")[1], "algorithmic_bytes": 8.0 * n * n,
+            "sweep": "every other cell of config 4: python bench.py --workload c4 (table under profiles/)"}
 
 
 def main():
@@ -384,12 +455,18 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 (default): the headline line, with config 5 as its `c5` block; c3 / c4 / c5: that configuration as the line")
     ap.add_argument("--paths", type=int, default=100_000)
     ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--strokes", type=int, default=50_000)
+    ap.add_argument("--scenes", type=int, default=4096, help="config 5: number of 1024x1024 scenes in the batch (all ranks together)")
     ap.add_argument("--cpu-sample", type=int, default=20000)
-    ap.add_argument("--ref-sample", type=int, default=4000)
+    ap.add_argument("--ref-budget-s", type=float, default=100.0, help="reference arm: wall-clock budget that bounds the number of whole-scene steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-composite", action="store_true", help="skip the K5 roofline leg (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 block of the default line (profiling runs)")
+    ap.add_argument("--quick", action="store_true", help="c4: one operator per cell group")
     ap.add_argument("--chunk", type=int, default=-1, help="recorder chunk size for the e2e leg (-1: library default, 0: one batch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

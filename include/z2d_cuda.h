@@ -221,6 +221,11 @@ int32_t z2d_surface_height(const z2d_sfc* sfc);
 uint32_t z2d_surface_format(const z2d_sfc* sfc);
 int32_t z2d_surface_upload(z2d_sfc* sfc, const void* host, size_t n);
 int32_t z2d_surface_download(z2d_sfc* sfc, void* host, size_t n); /* flushes + syncs */
+/* The same read-back without blocking the caller: everything recorded so far is enqueued, the copy into `host` (pinned memory
+ * for a truly asynchronous copy) runs on a separate stream after it and overlaps the calls recorded afterwards.  `host` is
+ * valid after the next z2d_sync.  The reference has no counterpart (its buffers ARE host memory, surface.zig:373): this is the
+ * boundary's replacement for reading `Surface.buf` of many surfaces (a batch of scenes) without one stall per surface. */
+int32_t z2d_surface_download_async(z2d_sfc* sfc, void* host, size_t n);
 void* z2d_surface_device_ptr(z2d_sfc* sfc); /* raw device pointer (interop) */
 
 /* Replaces the pixel transform of export_png.writePNGIDATStream / encodeRGBAVec (src/export_png.zig:150-373): the surface as the

@@ -3,6 +3,8 @@
 // contraction; the work is f64 edge evaluation, bit-sliced integer winding and
 // byte-wise compositing, bounded by HBM for the compositor and by the f64 /
 // integer pipes for coverage.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace z2d {
@@ -959,6 +961,7 @@ Z2D_D void fast_loop(const CompArgs& A, const float* __restrict__ lut) {
   const uint4* __restrict__ src = SURF ? reinterpret_cast<const uint4*>(A.ops[0].src.sdata + ((size_t)A.src_start_y * (size_t)A.ops[0].src.sw) * 4) : nullptr;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr bool kNoRead = OP == Z2D_OP_CLEAR || OP == Z2D_OP_SRC;
 #ifndef Z2D_COMP_STREAMS
 #define Z2D_COMP_STREAMS 2
 #endif
@@ -973,7 +976,7 @@ Z2D_D void fast_loop(const CompArgs& A, const float* __restrict__ lut) {
     uint4 v[Z2D_COMP_STREAMS], sv[Z2D_COMP_STREAMS];
 #pragma unroll
     for (int k = 0; k < Z2D_COMP_STREAMS; k++) {
-      v[k] = Z2D_LD(dst + i + k * stride);
+      v[k] = kNoRead ? make_uint4(0, 0, 0, 0) : Z2D_LD(dst + i + k * stride);  // clear / src never look at dst: write only
       sv[k] = SURF ? __ldg(src + i + k * stride) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
@@ -987,7 +990,7 @@ Z2D_D void fast_loop(const CompArgs& A, const float* __restrict__ lut) {
     for (int k = 0; k < Z2D_COMP_STREAMS; k++) Z2D_ST(dst + i + k * stride, v[k]);
   }
   for (; i < n4; i += stride) {
-    uint4 a = Z2D_LD(dst + i);
+    uint4 a = kNoRead ? make_uint4(0, 0, 0, 0) : Z2D_LD(dst + i);
     uint4 sa = make_uint4(0, 0, 0, 0);
     if (SURF) sa = __ldg(src + i);
     a.x = fast_px<PREC, OP, SURF>(fd, fs, lut, a.x, sc, sfc, sa.x);
@@ -1033,6 +1036,10 @@ __global__ void k_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw) 
 }
 
 __global__ void k_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t raw) { store_raw(data, fmt, idx, raw); }
+
+}  // namespace z2d
+#include "composite.cuh"
+namespace z2d {
 
 // ------------------------------------------------------------------------- launchers
 static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -1113,7 +1120,33 @@ void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   const unsigned cap = (unsigned)sm_count * 8u * 4u;  // grid-stride: a few waves of 8 resident CTAs per SM
   if (blocks > cap) blocks = cap;
   const CompOp& o0 = A.ops[0];
-  const bool one = vec && A.n_ops == 1 && !o0.has_dst && o0.has_src;
+  const bool full_rows = A.dst_start_x == 0 && A.scan_w == A.w;
+  const bool single = A.n_ops == 1 && !o0.has_dst && o0.has_src;
+  if (single && full_rows && A.fmt > Z2D_FMT_RGBA && o0.src.kind == Z2D_PARAM_PIXEL) {  // packed / 8-bit alpha, single pixel: byte table
+    const size_t chunks = (n * (size_t)fmt_bits(A.fmt) / 8 + 15) / 16 + 1;
+    unsigned lb = (unsigned)std::min<size_t>((chunks + 255) / 256, (size_t)sm_count * 8u);
+    k_composite_lut<<<lb ? lb : 1u, 256, 0, st>>>(A);
+    return;
+  }
+  if (single && full_rows && (o0.src.kind == Z2D_PARAM_GRADIENT || o0.src.kind == Z2D_PARAM_DITHER) && A.max_stops <= (uint32_t)kGenMaxStops) {
+    const int bits = fmt_bits(A.fmt);
+    const size_t chunks = (n * (size_t)bits / 8 + 15) / 16 + 1;
+    unsigned gb = (unsigned)std::min<size_t>((chunks + 255) / 256, (size_t)sm_count * 8u);
+    if (!gb) gb = 1;
+    const bool dith = o0.src.kind == Z2D_PARAM_DITHER, flt = A.precision != Z2D_PRECISION_INTEGER;
+    const int fc = bits == 32 ? 0 : bits == 8 ? 1 : 2;
+#define Z2D_GEN(FC, PR, DI) k_composite_gen<FC, PR, DI><<<gb, 256, 0, st>>>(A)
+#define Z2D_GEN_FC(FC)                                                                    \
+  if (!flt && !dith) Z2D_GEN(FC, Z2D_PRECISION_INTEGER, false);                            \
+  else if (!flt) Z2D_GEN(FC, Z2D_PRECISION_INTEGER, true);                                 \
+  else if (!dith) Z2D_GEN(FC, Z2D_PRECISION_FLOAT, false);                                 \
+  else Z2D_GEN(FC, Z2D_PRECISION_FLOAT, true);
+    if (fc == 0) { Z2D_GEN_FC(0) } else if (fc == 1) { Z2D_GEN_FC(1) } else { Z2D_GEN_FC(2) }
+#undef Z2D_GEN_FC
+#undef Z2D_GEN
+    return;
+  }
+  const bool one = vec && single;
   const bool fast_px_src = one && o0.src.kind == Z2D_PARAM_PIXEL;
   const bool fast_sfc_src = one && o0.src.kind == Z2D_PARAM_SURFACE && o0.src.sfmt <= Z2D_FMT_RGBA && o0.src.sw == A.w && A.src_start_x == 0;
   if (fast_px_src || fast_sfc_src) {

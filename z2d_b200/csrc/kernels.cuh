@@ -39,7 +39,8 @@ struct CompArgs {  // SurfaceCompositor.run after clipping (compositor.zig:347-3
   int32_t w, h;
   int32_t dst_start_x, dst_start_y, src_start_x, src_start_y;
   int32_t scan_w, rows;
-  int32_t y_origin, _pad;  // band destination: canvas row of its first row (patterns are evaluated in canvas space)
+  int32_t y_origin;        // band destination: canvas row of its first row (patterns are evaluated in canvas space)
+  uint32_t max_stops;      // largest stop count among the gradients of this call (k_composite_gen keeps <= 16 in shared memory)
   uint32_t n_ops, precision;
   GradTables T;
   CompOp ops[kMaxCompOps];

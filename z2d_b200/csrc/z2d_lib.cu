@@ -6,6 +6,7 @@
 // painter.zig:66-104, 214-304), splitting the node list into sub-paths and
 // converting gradient stops to their interpolation space once per call
 // (the reference redoes that per pixel, color_vector.zig:197-207).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -172,6 +173,9 @@ struct z2d_ctx {
   // device state
   InputSet in[2];
   cudaStream_t copy_stream = nullptr;  // H2D of batch inputs
+  cudaStream_t d2h_stream = nullptr;   // z2d_surface_download_async: read-backs that overlap the kernels of later batches
+  cudaEvent_t ev_d2h = nullptr;
+  bool d2h_pending = false;
   cudaEvent_t ev_up = nullptr;
   DevBuf d_node_sp, d_curve_list, d_sp_order, d_sp_keys;
   DevBuf d_blue, d_draws;
@@ -1025,6 +1029,8 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   for (auto& e : c->ev) cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
   for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
@@ -1067,6 +1073,11 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   }
   if (c->ev_up) cudaEventDestroy(c->ev_up);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) {
+    cudaStreamSynchronize(c->d2h_stream);
+    cudaStreamDestroy(c->d2h_stream);
+  }
+  if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
   for (Batch& b : c->bat) {
     b.nodes.release();
     b.subpaths.release();
@@ -1104,6 +1115,10 @@ int32_t z2d_sync(z2d_ctx* c) {
   int rc = flush(c);
   if (rc) return rc;
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->d2h_pending) {
+    CK(c, cudaStreamSynchronize(c->d2h_stream));
+    c->d2h_pending = false;
+  }
   return Z2D_OK;
 }
 
@@ -1202,6 +1217,10 @@ void z2d_surface_destroy(z2d_sfc* s) {
   cudaSetDevice(c->device);
   flush(c);
   cudaStreamSynchronize(c->stream);
+  if (c->d2h_pending) {
+    cudaStreamSynchronize(c->d2h_stream);
+    c->d2h_pending = false;
+  }
   cudaFree(s->data);
   delete s;
 }
@@ -1230,6 +1249,19 @@ int32_t z2d_surface_download(z2d_sfc* s, void* host, size_t n) {
   if (rc) return rc;
   CK(c, cudaMemcpyAsync(host, s->data, n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_download_async(z2d_sfc* s, void* host, size_t n) {
+  if (!s || !host || n != s->bytes) return Z2D_E_INVALID_ARG;
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);  // everything recorded so far is on the stream; the copy waits for it and nothing later waits for the copy
+  if (rc) return rc;
+  CK(c, cudaEventRecord(c->ev_d2h, c->stream));
+  CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_d2h, 0));
+  CK(c, cudaMemcpyAsync(host, s->data, n, cudaMemcpyDeviceToHost, c->d2h_stream));
+  c->d2h_pending = true;
   return Z2D_OK;
 }
 
@@ -1778,6 +1810,7 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   CK(c, upload(c, c->d_comp_grads, grads.data(), grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_comp_stop_off, offs.data(), offs.size() * 4));
   CK(c, upload(c, c->d_comp_stop_col, cols.data(), cols.size() * sizeof(float4)));
+  for (const DevGrad& g : grads) A.max_stops = std::max(A.max_stops, g.n_stops);
   A.T = tables(c, c->d_comp_grads, c->d_comp_stop_off, c->d_comp_stop_col);
   launch_composite(A, c->sm_count, c->stream);
   CK(c, cudaGetLastError());

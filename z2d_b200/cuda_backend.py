@@ -48,6 +48,7 @@ def load_library():
         "z2d_surface_format": (C.c_uint32, [vp]),
         "z2d_surface_upload": (C.c_int32, [vp, vp, C.c_size_t]),
         "z2d_surface_download": (C.c_int32, [vp, vp, C.c_size_t]),
+        "z2d_surface_download_async": (C.c_int32, [vp, vp, C.c_size_t]),
         "z2d_surface_device_ptr": (vp, [vp]),
         "z2d_surface_export_size": (C.c_size_t, [vp, C.c_uint32]),
         "z2d_surface_export": (C.c_int32, [vp, C.c_uint32, vp, C.c_size_t]),
@@ -71,7 +72,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
-                    "z2d_surface_download", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel",
+                    "z2d_surface_download", "z2d_surface_download_async", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel",
                     "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
 
 

@@ -33,6 +33,8 @@ PATTERN_DT = _np_dtype(abi.PatternPOD)
 DRAWCMD_DT = _np_dtype(abi.DrawCmdPOD)
 STROKEOPTS_DT = _np_dtype(abi.StrokeOptsPOD)
 FILLOPTS_DT = _np_dtype(abi.FillOptsPOD)
+GRADIENT_DT = _np_dtype(abi.GradientPOD)
+STOP_DT = _np_dtype(abi.StopPOD)
 
 
 class FillScene:
@@ -214,35 +216,107 @@ def stroke_paths_scene(n_paths=50_000, size=2048, seed=0x7A326403, aa=AntiAliasM
                  np.arange(n_paths, dtype=np.int64), keep=(dashes,))
 
 
-def mixed_scene(scene_index, size=1024, n_fills=32, n_strokes=24, seed_base=0x7A326405):
-    """BASELINE config 5 shape: one SVG-like scene of ordered fills (config-2 generator, r 8-256) and strokes (config-3
-    generator), interleaved fill/stroke in submission order; seed = seed_base + scene."""
-    seed = (seed_base + scene_index) & 0xFFFFFFFF
-    f = cubic_paths_scene(n_fills, size, seed=seed, r_log2=(3.0, 8.0))
-    st = stroke_paths_scene(n_strokes, size, seed=seed ^ 0x5A5A5A5A)
-    n = n_fills + n_strokes
-    # interleave: draw order f0 s0 f1 s1 ... then the remaining fills
-    order = []
-    fi = si = 0
-    while fi < n_fills or si < n_strokes:
-        if fi < n_fills:
-            order.append((0, fi)); fi += 1
-        if si < n_strokes:
-            order.append((1, si)); si += 1
-    nodes = np.concatenate([f.nodes, st.nodes])
-    f_off, s_off = f.node_off, st.node_off + len(f.nodes)
-    node_lo = np.array([f_off[i] if k == 0 else s_off[i] for k, i in order], dtype=np.int64)
-    node_hi = np.array([f_off[i + 1] if k == 0 else s_off[i + 1] for k, i in order], dtype=np.int64)
-    # nodes must be contiguous per draw and node_off monotone: rebuild the node array in draw order
-    parts = [nodes[a:b] for a, b in zip(node_lo, node_hi)]
-    nodes2 = np.concatenate(parts)
-    node_off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+_ORDER_CACHE = {}
+
+
+def _interleave_order(counts):
+    """Proportional round-robin over the parts (draw order f s f s g f s f ...): [(part, index in part), ...]."""
+    if counts not in _ORDER_CACHE:
+        order, taken = [], [0] * len(counts)
+        for _ in range(sum(counts)):
+            k = min((i for i in range(len(counts)) if taken[i] < counts[i]), key=lambda i: (taken[i] + 1) / counts[i])  # furthest behind its share
+            order.append((k, taken[k]))
+            taken[k] += 1
+        _ORDER_CACHE[counts] = order
+    return _ORDER_CACHE[counts]
+
+
+def gradient_fills_scene(n=8, size=1024, seed=0x7A326405, aa=AntiAliasMode.default, op=Operator.src_over):
+    """n gradient-filled shapes (2 linear, 3 radial, 3 conic per 8; rectangles and ellipses alternate),
+    three random translucent stops each, identity pattern transformation, non-zero rule."""
+    rng = np.random.default_rng(seed)
+    kinds = [abi.GradientType.linear, abi.GradientType.linear, abi.GradientType.radial, abi.GradientType.radial,
+             abi.GradientType.radial, abi.GradientType.conic, abi.GradientType.conic, abi.GradientType.conic]
+    K = 0.5522847498307936  # cubic approximation of a quarter circle
+    tags, pts, node_off = [], [], [0]
+    grads = np.zeros(n, dtype=GRADIENT_DT)
+    stops = np.zeros((n, 3), dtype=STOP_DT)
+    for i in range(n):
+        cx, cy = rng.uniform(0, size, 2)
+        rx, ry = rng.uniform(32, 256, 2)
+        cx, cy, rx, ry = (float(np.round(v * 16) / 16) for v in (cx, cy, rx, ry))
+        q = lambda v: float(np.round(v * 16) / 16)  # noqa: E731
+        if i % 2 == 0:  # rectangle
+            corners = [(cx - rx, cy - ry), (cx + rx, cy - ry), (cx + rx, cy + ry), (cx - rx, cy + ry)]
+            tags.append(int(NodeTag.move_to)); pts.append((corners[0][0], corners[0][1], 0, 0, 0, 0))
+            for c in corners[1:]:
+                tags.append(int(NodeTag.line_to)); pts.append((c[0], c[1], 0, 0, 0, 0))
+        else:  # ellipse: four cubic arcs
+            tags.append(int(NodeTag.move_to)); pts.append((cx + rx, cy, 0, 0, 0, 0))
+            arcs = [((cx + rx, cy + K * ry), (cx + K * rx, cy + ry), (cx, cy + ry)), ((cx - K * rx, cy + ry), (cx - rx, cy + K * ry), (cx - rx, cy)),
+                    ((cx - rx, cy - K * ry), (cx - K * rx, cy - ry), (cx, cy - ry)), ((cx + K * rx, cy - ry), (cx + rx, cy - K * ry), (cx + rx, cy))]
+            for c1, c2, e in arcs:
+                tags.append(int(NodeTag.curve_to)); pts.append((q(c1[0]), q(c1[1]), q(c2[0]), q(c2[1]), q(e[0]), q(e[1])))
+        first = pts[node_off[-1]]
+        tags.append(int(NodeTag.close_path)); pts.append((0, 0, 0, 0, 0, 0))
+        tags.append(int(NodeTag.move_to)); pts.append((first[0], first[1], 0, 0, 0, 0))  # Path.close leaves a move_to behind
+        node_off.append(len(tags))
+        kind = kinds[i % 8]
+        grads["type"][i] = int(kind)
+        grads["method"][i] = int(abi.Interp.linear_rgb)
+        grads["polar"][i] = int(abi.Polar.shorter)
+        grads["n_stops"][i] = 3
+        if kind == abi.GradientType.linear:
+            grads["geom"][i] = (cx - rx, cy - ry, cx + rx, cy + ry, 0, 0)
+        elif kind == abi.GradientType.radial:
+            grads["geom"][i] = (cx, cy, 0.0, cx, cy, max(rx, ry))
+        else:
+            grads["geom"][i] = (cx, cy, float(rng.uniform(0, 2 * np.pi)), 0, 0, 0)
+        grads["inv_ctm"][i] = (1, 0, 0, 1, 0, 0)
+        stops["offset"][i] = (0.0, 0.5, 1.0)
+        stops["color"]["space"][i] = int(abi.ColorSpace.linear_rgb)
+        col = rng.uniform(0, 1, (3, 4)).astype(np.float32)
+        col[:, 3] = rng.uniform(0.5, 1.0, 3)
+        stops["color"]["c"][i] = col
+    grads["stops"] = stops.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(3 * STOP_DT.itemsize)
+    nodes = np.zeros(len(tags), dtype=NODE_DT)
+    nodes["tag"] = np.array(tags, dtype=np.uint32)
+    nodes["p"] = np.array(pts, dtype=np.float64)
     patterns = np.zeros(n, dtype=PATTERN_DT)
-    kind = np.zeros(n, dtype=np.uint32)
-    opt_index = np.zeros(n, dtype=np.int64)
-    fopts = np.frombuffer(f.fill_opts, dtype=FILLOPTS_DT).copy()
+    patterns["kind"] = int(PatternKind.gradient)
+    patterns["gradient"] = grads.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(GRADIENT_DT.itemsize)
+    fo = np.zeros(1, dtype=FILLOPTS_DT)
+    fo["anti_aliasing_mode"], fo["fill_rule"], fo["op"], fo["precision"], fo["tolerance"] = int(aa), int(FillRule.non_zero), int(op), int(Precision.integer), 0.1
+    return Scene(size, size, nodes, np.array(node_off, dtype=np.int64), patterns, np.zeros(n, dtype=np.uint32), fo,
+                 np.zeros(0, dtype=STROKEOPTS_DT), np.zeros(n, dtype=np.int64), keep=(grads, stops))
+
+
+def mixed_scene(scene_index, size=1024, n_fills=32, n_strokes=24, n_gradients=8, seed_base=0x7A326405):
+    """BASELINE config 5 shape: one SVG-like scene of 64 ordered draw calls -- 32 fills (config-2 generator,
+    r 8-256), 24 strokes (config-3 generator) and 8 gradient fills (2 linear, 3 radial, 3 conic; rectangles and ellipses),
+    interleaved in submission order; seed = seed_base + scene."""
+    seed = (seed_base + scene_index) & 0xFFFFFFFF
+    parts = [cubic_paths_scene(n_fills, size, seed=seed, r_log2=(3.0, 8.0)), stroke_paths_scene(n_strokes, size, seed=seed ^ 0x5A5A5A5A)]
+    if n_gradients:
+        parts.append(gradient_fills_scene(n_gradients, size, seed=seed ^ 0x3C3C3C3C))
+    counts = tuple(p.n for p in parts)
+    order = _interleave_order(counts)
+    total = sum(counts)
+    node_parts, node_off = [], [0]
+    patterns = np.zeros(total, dtype=PATTERN_DT)
+    kind = np.zeros(total, dtype=np.uint32)
+    opt_index = np.zeros(total, dtype=np.int64)
+    fill_opts_list = [np.frombuffer(parts[0].fill_opts, dtype=FILLOPTS_DT).copy()]
+    g_base = len(fill_opts_list[0])
+    if n_gradients:
+        fill_opts_list.append(parts[2].fill_opts)
     for j, (k, i) in enumerate(order):
-        patterns[j] = f.patterns[i] if k == 0 else st.patterns[i]
-        kind[j] = k
-        opt_index[j] = f.opt_index[i] if k == 0 else i
-    return Scene(size, size, nodes2, node_off, patterns, kind, fopts, st.stroke_opts, opt_index, keep=st.keep)
+        p = parts[k]
+        node_parts.append(p.nodes[p.node_off[i]:p.node_off[i + 1]])
+        node_off.append(node_off[-1] + len(node_parts[-1]))
+        patterns[j] = p.patterns[i]
+        kind[j] = 1 if k == 1 else 0
+        opt_index[j] = p.opt_index[i] if k == 0 else (i if k == 1 else g_base + p.opt_index[i])
+    keep = tuple(parts[1].keep) + (tuple(parts[2].keep) if n_gradients else ())
+    return Scene(size, size, np.concatenate(node_parts), np.array(node_off, dtype=np.int64), patterns, kind,
+                 np.concatenate(fill_opts_list), parts[1].stroke_opts, opt_index, keep=keep)
