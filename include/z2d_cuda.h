@@ -258,7 +258,12 @@ int32_t z2d_stroke(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,
 
 /* compositor.SurfaceCompositor.run (compositor.zig:302-440).  Infallible in
  * the reference (invalid combinations are silent no-ops); the status only
- * reports device/argument errors. */
+ * reports device/argument errors.  Z2D_E_INVALID_ARG also for a surface
+ * parameter that does not cover the composited rectangle (the clip of
+ * compositor.zig:347-374 only looks at ops[0].src; the reference would read
+ * past the smaller surface's strides) and for the destination used as a
+ * parameter of itself at a non-zero offset (there the reference's result
+ * depends on its scanline / vector order). */
 int32_t z2d_composite(z2d_ctx* ctx, z2d_sfc* dst, int32_t dst_x, int32_t dst_y,
                       const z2d_comp_op* ops, size_t n_ops, uint32_t precision);
 

@@ -5,7 +5,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from z2d_b200 import abi, workloads
+from z2d_b200 import abi, host, workloads
+from z2d_b200.abi import Format
 from z2d_b200.host import Pixel, Surface
 
 pytestmark = pytest.mark.gpu
@@ -113,3 +114,54 @@ def test_parallel_recorder_equals_one_by_one_calls(cuda):
     assert np.array_equal(got, ref)
     a.deinit()
     b.deinit()
+
+
+def test_composite_surface_params_must_cover_the_rectangle(cuda):
+    """z2d_composite clips against ops[0].src only (compositor.zig:347-374); any other surface parameter that is smaller than the
+    composited rectangle, and the destination as a parameter of itself at an offset, is refused instead of read out of bounds."""
+    import pytest as _pytest
+    from tests import specs
+    z = specs.bind(cuda)
+    dst = z.Surface(Format.rgba, 32, 32)
+    big = z.SurfacePixel(host.Pixel.rgba(10, 20, 30, 40), 32, 32)
+    small = z.SurfacePixel(host.Pixel.rgba(10, 20, 30, 40), 16, 16)
+    with _pytest.raises(abi.InvalidArg):  # second operation reads a smaller source
+        z.SurfaceCompositor.run(dst, 0, 0, [z.Operation(abi.Operator.src_over, src=z.Param.surface(big)),
+                                            z.Operation(abi.Operator.src_over, src=z.Param.surface(small))])
+    with _pytest.raises(abi.InvalidArg):  # dst override smaller than the destination region
+        z.SurfaceCompositor.run(dst, 0, 0, [z.Operation(abi.Operator.dst_in, dst=z.Param.surface(small), src=z.Param.surface(big))])
+    with _pytest.raises(abi.InvalidArg):  # the destination shifted onto itself
+        z.SurfaceCompositor.run(dst, 3, 0, [z.Operation(abi.Operator.src_over, src=z.Param.surface(dst))])
+    z.SurfaceCompositor.run(dst, 0, 0, [z.Operation(abi.Operator.plus, src=z.Param.surface(dst))])  # pixel for pixel is fine
+    assert not dst.download().any()
+
+
+@pytest.mark.parametrize("dst_fmt,src_fmt", [(Format.rgba, Format.rgba), (Format.rgba, Format.alpha8), (Format.alpha8, Format.rgba),
+                                             (Format.alpha4, Format.alpha8), (Format.rgb, Format.alpha2)])
+def test_surface_composite_at_negative_and_positive_offsets_matches_oracle(cuda, oracle, dst_fmt, src_fmt):
+    """Surface.composite / SurfaceCompositor.run with a surface source placed partly outside the destination on every side
+    (compositor.zig:347-374: negative offsets start the source at -offset), byte for byte."""
+    from tests import specs
+    rng = np.random.default_rng(11)
+
+    def content(fmt, w, h):
+        data = rng.integers(0, 256, abi.surface_byte_len(fmt, w, h), dtype=np.uint8)
+        if fmt == Format.rgba:
+            px = data.reshape(-1, 4).astype(np.int32)
+            px[:, :3] = px[:, :3] * px[:, 3:4] // 255
+            data = px.astype(np.uint8).reshape(-1)
+        return data
+
+    d0, s0 = content(dst_fmt, 37, 29), content(src_fmt, 23, 31)
+    for dx, dy in ((-5, -3), (20, -7), (-11, 9), (30, 25), (0, 0), (3, 2)):
+        for op in (abi.Operator.src_over, abi.Operator.xor, abi.Operator.dst_in):
+            res = []
+            for z in (specs.bind(cuda), specs.bind(oracle)):
+                dst, src = z.Surface(dst_fmt, 37, 29), z.Surface(src_fmt, 23, 31)
+                dst.upload(d0.copy())
+                src.upload(s0.copy())
+                z.SurfaceCompositor.run(dst, dx, dy, [z.Operation(op, src=z.Param.surface(src))])
+                res.append(dst.download().copy())
+            if dst_fmt == Format.rgb:
+                res = [r.reshape(-1, 4)[:, :3] for r in res]
+            assert np.array_equal(res[0], res[1]), f"{dst_fmt.name} <- {src_fmt.name} at ({dx},{dy}) {op.name}"

@@ -1151,7 +1151,9 @@ int32_t z2d_replay(z2d_ctx* c) {
   cudaSetDevice(c->device);
   int rc = flush(c);
   if (rc) return rc;
-  return run_pipeline(c, true);
+  rc = run_pipeline(c, true);
+  if (c->last.valid) cudaEventRecord(c->in[c->last.set].done, c->stream);  // the next upload into this input set waits for the replay
+  return rc;
 }
 
 // ------------------------------------------------------------------------- surfaces
@@ -1786,12 +1788,19 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   std::vector<DevGrad> grads;
   std::vector<float> offs;
   std::vector<float4> cols;
-  auto conv = [&](const z2d_comp_param& p, DevSrc& s, uint32_t& has) -> int {
+  auto conv = [&](const z2d_comp_param& p, DevSrc& s, uint32_t& has, bool is_dst) -> int {
     has = p.kind != Z2D_PARAM_NONE;
     if (!has) return Z2D_OK;
     if (p.kind == Z2D_PARAM_SURFACE) {
       const z2d_sfc* ss = (const z2d_sfc*)p.surface;
       if (!ss || ss->ctx != c) return Z2D_E_INVALID_ARG;
+      // every surface parameter must cover the rectangle it is read over: sources in source space, dst overrides in
+      // destination space (the clipping above only looked at ops[0].src)
+      const int need_x = (is_dst ? A.dst_start_x : A.src_start_x) + A.scan_w, need_y = (is_dst ? A.dst_start_y : A.src_start_y) + A.rows;
+      if (ss->w < need_x || ss->h < need_y) return Z2D_E_INVALID_ARG;
+      // the destination itself as a parameter is only well defined pixel for pixel (the reference's result for a shifted
+      // self-composite depends on its scanline / vector order)
+      if (ss == dst && (dst_x != 0 || dst_y != 0)) return Z2D_E_INVALID_ARG;
       memset(&s, 0, sizeof s);
       s.kind = Z2D_PARAM_SURFACE;
       s.sdata = ss->data;
@@ -1804,8 +1813,8 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
   };
   for (size_t k = 0; k < n_ops; k++) {
     A.ops[k].op = ops[k].op;
-    if ((rc = conv(ops[k].dst, A.ops[k].dst, A.ops[k].has_dst))) return rc;
-    if ((rc = conv(ops[k].src, A.ops[k].src, A.ops[k].has_src))) return rc;
+    if ((rc = conv(ops[k].dst, A.ops[k].dst, A.ops[k].has_dst, true))) return rc;
+    if ((rc = conv(ops[k].src, A.ops[k].src, A.ops[k].has_src, false))) return rc;
   }
   CK(c, upload(c, c->d_comp_grads, grads.data(), grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_comp_stop_off, offs.data(), offs.size() * 4));

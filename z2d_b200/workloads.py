@@ -296,27 +296,36 @@ def mixed_scene(scene_index, size=1024, n_fills=32, n_strokes=24, n_gradients=8,
     r 8-256), 24 strokes (config-3 generator) and 8 gradient fills (2 linear, 3 radial, 3 conic; rectangles and ellipses),
     interleaved in submission order; seed = seed_base + scene."""
     seed = (seed_base + scene_index) & 0xFFFFFFFF
-    parts = [cubic_paths_scene(n_fills, size, seed=seed, r_log2=(3.0, 8.0)), stroke_paths_scene(n_strokes, size, seed=seed ^ 0x5A5A5A5A)]
+    parts = []  # (what, scene)
+    if n_fills:
+        parts.append(("fill", cubic_paths_scene(n_fills, size, seed=seed, r_log2=(3.0, 8.0))))
+    if n_strokes:
+        parts.append(("stroke", stroke_paths_scene(n_strokes, size, seed=seed ^ 0x5A5A5A5A)))
     if n_gradients:
-        parts.append(gradient_fills_scene(n_gradients, size, seed=seed ^ 0x3C3C3C3C))
-    counts = tuple(p.n for p in parts)
+        parts.append(("gradient", gradient_fills_scene(n_gradients, size, seed=seed ^ 0x3C3C3C3C)))
+    counts = tuple(p.n for _, p in parts)
     order = _interleave_order(counts)
     total = sum(counts)
     node_parts, node_off = [], [0]
     patterns = np.zeros(total, dtype=PATTERN_DT)
     kind = np.zeros(total, dtype=np.uint32)
     opt_index = np.zeros(total, dtype=np.int64)
-    fill_opts_list = [np.frombuffer(parts[0].fill_opts, dtype=FILLOPTS_DT).copy()]
-    g_base = len(fill_opts_list[0])
-    if n_gradients:
-        fill_opts_list.append(parts[2].fill_opts)
+    fill_opts_list, fill_base, stroke_opts, keep = [], {}, np.zeros(0, dtype=STROKEOPTS_DT), ()
+    for what, p in parts:
+        if what == "stroke":
+            stroke_opts = p.stroke_opts
+        else:
+            fo = p.fill_opts if isinstance(p.fill_opts, np.ndarray) else np.frombuffer(p.fill_opts, dtype=FILLOPTS_DT).copy()
+            fill_base[what] = sum(len(x) for x in fill_opts_list)
+            fill_opts_list.append(fo)
+        keep = keep + tuple(getattr(p, "keep", ()))
     for j, (k, i) in enumerate(order):
-        p = parts[k]
+        what, p = parts[k]
         node_parts.append(p.nodes[p.node_off[i]:p.node_off[i + 1]])
         node_off.append(node_off[-1] + len(node_parts[-1]))
         patterns[j] = p.patterns[i]
-        kind[j] = 1 if k == 1 else 0
-        opt_index[j] = p.opt_index[i] if k == 0 else (i if k == 1 else g_base + p.opt_index[i])
-    keep = tuple(parts[1].keep) + (tuple(parts[2].keep) if n_gradients else ())
-    return Scene(size, size, np.concatenate(node_parts), np.array(node_off, dtype=np.int64), patterns, kind,
-                 np.concatenate(fill_opts_list), parts[1].stroke_opts, opt_index, keep=keep)
+        kind[j] = 1 if what == "stroke" else 0
+        opt_index[j] = i if what == "stroke" else fill_base[what] + p.opt_index[i]
+    fill_opts = np.concatenate(fill_opts_list) if fill_opts_list else np.zeros(0, dtype=FILLOPTS_DT)
+    return Scene(size, size, np.concatenate(node_parts), np.array(node_off, dtype=np.int64), patterns, kind, fill_opts, stroke_opts, opt_index,
+                 keep=keep)
