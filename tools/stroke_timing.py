@@ -27,4 +27,4 @@ for it in range(8):
     if it >= 2 and (best is None or st["ms_total"] < best["ms_total"]):
         best = st
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in best.items() if k in ("draws", "edges", "band_edges", "tile_pairs", "crossings", "covered_px", "ms_flatten", "ms_bin", "ms_lists", "ms_raster", "ms_total")})
-print(f"{best['draws'] / best['ms_total'] / 1e3:.2f} M strokes/s, {best['covered_px'] / best['ms_total'] / 1e6:.2f} Gpix/s")
+print(best["ms_raster"], best["ms_flatten"], f"{best['draws'] / best['ms_total'] / 1e3:.2f} M strokes/s, {best['covered_px'] / best['ms_total'] / 1e6:.2f} Gpix/s")

@@ -96,112 +96,6 @@ __global__ void __launch_bounds__(256) k_composite_lut(const __grid_constant__ C
 }
 
 // =============================================================================== k_composite_gen
-constexpr int kGenMaxStops = 16;
-
-// gradient.getOffset with the row-invariant terms computed once per row (identity inverse CTM; otherwise grad_offset)
-struct GradRowEval {
-  const DevGrad* g;
-  bool hoist;
-  double ex, ey, inv_dist, eysy;          // linear
-  double r0dr, nr0sq, pdy, pdycdy, pdy2;  // radial
-  double dy;                              // conic
-  int y;
-  Z2D_D void init(const DevGrad* gg) {
-    g = gg;
-    hoist = g->inv_identity != 0u;
-    if (g->type == Z2D_GRADIENT_LINEAR) {
-      ex = g->geom[2] - g->geom[0];
-      ey = g->geom[3] - g->geom[1];
-      double dist = 0.0;
-      dist += ex * ex;
-      dist += ey * ey;
-      if (dist == 0.0) hoist = false;  // (-1 for every pixel: leave it to grad_offset)
-      inv_dist = 1.0 / dist;
-    } else if (g->type == Z2D_GRADIENT_RADIAL) {
-      r0dr = g->inner_r * g->dr;
-      nr0sq = -g->inner_r * g->inner_r;
-      if (g->inner_r == 0.0 && g->outer_r == 0.0) hoist = false;
-    }
-  }
-  Z2D_D void set_row(int yy) {
-    y = yy;
-    const double py = (double)yy + 0.5;
-    if (g->type == Z2D_GRADIENT_LINEAR) {
-      const double sy = py - g->geom[1];
-      eysy = ey * sy;
-    } else if (g->type == Z2D_GRADIENT_RADIAL) {
-      pdy = py - g->geom[1];
-      pdycdy = pdy * g->cdy;
-      pdy2 = pdy * pdy;
-    } else {
-      dy = py - g->geom[1];
-    }
-  }
-  Z2D_D float offset(int x) const {
-    if (!hoist) return grad_offset(*g, x, y);
-    const double px = (double)x + 0.5;
-    if (g->type == Z2D_GRADIENT_LINEAR) {  // gradient.zig:349-372
-      const double sx = px - g->geom[0];
-      double d = 0.0;
-      d += ex * sx;
-      d += eysy;
-      double v = d * inv_dist;
-      v = v < 1.0 ? v : 1.0;
-      v = v > 0.0 ? v : 0.0;
-      return (float)v;
-    }
-    if (g->type == Z2D_GRADIENT_RADIAL) {  // gradient.zig:605-648
-      const double pdx = px - g->geom[0];
-      double b = 0.0;
-      b += pdx * g->cdx;
-      b += pdycdy;
-      b += r0dr;
-      double c = 0.0;
-      c += pdx * pdx;
-      c += pdy2;
-      c += nr0sq;
-      double t;
-      if (g->a == 0.0) {
-        if (b == 0.0) return -1.0f;
-        t = 0.5 * c / b;
-        if (!(t * g->dr >= g->min_dr)) return -1.0f;
-      } else {
-        double discr = 0.0;
-        discr += b * b;
-        discr += g->a * -c;
-        if (!(discr >= 0.0)) return -1.0f;
-        const double sq = sqrt(discr);
-        const double t0 = (b + sq) * g->inv_a, t1 = (b - sq) * g->inv_a;
-        if (t0 * g->dr >= g->min_dr)
-          t = t0;
-        else if (t1 * g->dr >= g->min_dr)
-          t = t1;
-        else
-          return -1.0f;
-      }
-      t = t < 1.0 ? t : 1.0;
-      t = t > 0.0 ? t : 0.0;
-      return (float)t;
-    }
-    const double dx = px - g->geom[0];  // gradient.zig:731-741
-    const double two_pi = 6.283185307179586476925286766559;
-    double ang = fmod(atan2(dy, dx) - g->geom[2], two_pi);
-    if (ang < 0.0) ang += two_pi;
-    return (float)(ang / two_pi);
-  }
-};
-
-// alpha of the interpolated colour only: every interpolation method ends in the same f32 lerp of the stop alphas
-// (color_vector.zig:295-342, 404-448), and both encodings keep it as round(255 * a) (premultiplication leaves alpha alone)
-Z2D_D float hit_alpha(const StopHit& h) { return lerpf(h.c0.w, h.c1.w, h.t); }
-
-template <int PREC, bool DITHER, bool ALPHA_ONLY>
-struct GenSrc {
-  RGBA16 si;
-  RGBAF sf;
-};
-
-// FC: 0 = 32-bit formats, 1 = alpha8, 2 = alpha4 / alpha2 / alpha1
 #ifndef Z2D_GEN_MIN_CTAS
 #define Z2D_GEN_MIN_CTAS 4  // 64 registers: 0.67 ms against 0.90 ms at 121 registers / 2 CTAs (rgba, linear gradient, 8192^2)
 #endif
@@ -211,24 +105,11 @@ __global__ void __launch_bounds__(256, Z2D_GEN_MIN_CTAS) k_composite_gen(const _
   __shared__ float s_off[kGenMaxStops];
   __shared__ float4 s_col[kGenMaxStops];
   const DevSrc& src = A.ops[0].src;
-  const bool has_grad = !DITHER || src.dither_source == Z2D_DITHER_SRC_GRADIENT;
-  if (has_grad) {
-    const DevGrad& g0 = A.T.grads[src.grad];
-    if (threadIdx.x == 0) {
-      sg = g0;
-      sg.stop_base = 0;
-    }
-    if (threadIdx.x < g0.n_stops) {
-      s_off[threadIdx.x] = A.T.stop_offsets[g0.stop_base + threadIdx.x];
-      s_col[threadIdx.x] = A.T.stop_colors[g0.stop_base + threadIdx.x];
-    }
-  }
+  const GradTables T = pattern_stage(src, A.T, &sg, s_off, s_col, (int)threadIdx.x, (int)blockDim.x);
   __syncthreads();
-  GradTables T = A.T;
-  T.stop_offsets = s_off;
-  T.stop_colors = s_col;
-  GradRowEval ev;
-  if (has_grad) ev.init(&sg);
+  PatternSampler ps;
+  ps.init(&src, &sg, T);
+  const bool has_grad = ps.has_grad;
   const uint32_t op = A.ops[0].op, fmt = A.fmt;
   const int bits = FC == 0 ? 32 : FC == 1 ? 8 : fmt_bits(fmt);
   const Fmt32 fd = fmt32_of(fmt);
@@ -237,48 +118,14 @@ __global__ void __launch_bounds__(256, Z2D_GEN_MIN_CTAS) k_composite_gen(const _
   const int ppc = 128 / bits;  // pixels per 16-byte chunk
   const size_t c_lo = first_px / (size_t)ppc, c_hi = (end_px + (size_t)ppc - 1) / (size_t)ppc;
   uint4* q = reinterpret_cast<uint4*>(A.data);
-  const float dscale = DITHER ? 1.0f / (float)((1 << src.dither_scale) - 1) : 0.0f;
+  (void)DITHER;
 
-  // one source sample: integer pipeline -> premultiplied RGBA8 (alpha only when the destination keeps nothing else),
-  // float pipeline -> de-multiplied linear colour (compositor.zig:1086-1131)
-  auto sample = [&](int x, int y, RGBA16& si, RGBAF& sf) Z2D_LAMBDA {
-    if (!DITHER) {
-      const StopHit hit = grad_search(sg, T, ev.offset(x));
-      if (PREC == Z2D_PRECISION_INTEGER) {
-        if (FC != 0) si = RGBA16{0, 0, 0, round255(hit_alpha(hit))};
-        else si = grad_encode(sg, hit);
-      } else {
-        if (FC != 0) sf = RGBAF{0.f, 0.f, 0.f, hit_alpha(hit)};
-        else sf = grad_linear(sg, hit);
-      }
-      return;
-    }
-    RGBAF c;
-    if (has_grad) {
-      const StopHit hit = grad_search(sg, T, ev.offset(x));
-      if (FC != 0) c = RGBAF{0.f, 0.f, 0.f, hit_alpha(hit)};
-      else c = grad_linear(sg, hit);
-    } else {
-      c = RGBAF{src.dcol[0], src.dcol[1], src.dcol[2], src.dcol[3]};
-    }
-    if (src.dither_type == Z2D_DITHER_BAYER || src.dither_type == Z2D_DITHER_BLUE_NOISE) {
-      const float m = src.dither_type == Z2D_DITHER_BAYER ? m_bayer(x, y) : m_blue(T, x, y);
-      const float ms = m * dscale;
-      if (FC != 0) c.a = clamp01(c.a + ms);
-      else c = RGBAF{clamp01(c.r + ms), clamp01(c.g + ms), clamp01(c.b + ms), clamp01(c.a + ms)};
-    }
-    if (PREC == Z2D_PRECISION_INTEGER) {
-      if (FC != 0) si = RGBA16{0, 0, 0, round255(c.a)};
-      else si = premul16(encode_raw(c));
-    } else {
-      sf = c;
-    }
-  };
   // one destination pixel (raw sample in the destination format) -> new raw sample
   auto blend = [&](uint32_t raw, int x, int y) Z2D_LAMBDA -> uint32_t {
     RGBA16 si{0, 0, 0, 0};
     RGBAF sf{0.f, 0.f, 0.f, 0.f};
-    sample(x, y, si, sf);
+    if (PREC == Z2D_PRECISION_INTEGER) si = ps.template sample_int<FC != 0>(x, y);
+    else sf = ps.template sample_float<FC != 0>(x, y);
     if (FC == 0) {
       const RGBA16 d = unpack32(fd, raw);
       if (PREC == Z2D_PRECISION_INTEGER) return pack32(fd, int_op_sw(op, d, si));
@@ -303,7 +150,7 @@ __global__ void __launch_bounds__(256, Z2D_GEN_MIN_CTAS) k_composite_gen(const _
     const size_t p0 = c * (size_t)ppc;
     int y = (int)(p0 / (size_t)W), x = (int)(p0 - (size_t)y * (size_t)W);
     y += A.y_origin;  // patterns are evaluated at the canvas row (band destinations)
-    if (has_grad) ev.set_row(y);
+    if (has_grad) ps.set_row(y);
     const bool interior = p0 >= first_px && p0 + (size_t)ppc <= end_px;
 #pragma unroll 1
     for (int k = 0; k < ppc; k++) {
@@ -315,7 +162,7 @@ __global__ void __launch_bounds__(256, Z2D_GEN_MIN_CTAS) k_composite_gen(const _
       if (++x == W) {
         x = 0;
         ++y;
-        if (has_grad) ev.set_row(y);
+        if (has_grad) ps.set_row(y);
       }
     }
     q[c] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -860,6 +860,7 @@ template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const u
                                             const uint32_t*, uint4*, const uint32_t*, const uint2*);
 
 }  // namespace z2d
+#include "pattern.cuh"
 #include "raster.cuh"
 namespace z2d {
 
@@ -1108,8 +1109,10 @@ void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* s
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {
   if (n_draws) k_edge_sim<<<blocks_for(n_draws, 64), 64, 0, st>>>(draws, n_draws, sfcs, edges, sp_off, perm, xs, rows);
 }
-void launch_raster(const RasterArgs& A, cudaStream_t st) {
-  if (A.n_tiles) k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
+void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st) {
+  if (!A.n_tiles) return;
+  if (rich) k_raster_tiles_rich<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
+  else k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
 }
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   const size_t n = (size_t)A.scan_w * (size_t)A.rows;

@@ -76,7 +76,8 @@ void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const
 // exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);
-void launch_raster(const RasterArgs& A, cudaStream_t st);
+// rich: the batch holds strokes or gradient / dither sources (k_raster_tiles_rich, see raster.cuh)
+void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st);
 // isolated single-draw modes (slowpath.cuh)
 void launch_hairline(const DevSurface* sfcs, const DevDraw* draws, uint32_t draw_index, const z2d_node* nodes, uint32_t node_begin,
                      uint32_t node_end, const double* dashes, const GradTables& T, cudaStream_t st);

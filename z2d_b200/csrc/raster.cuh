@@ -102,6 +102,44 @@ Z2D_D uint32_t composite_cov(const DrawHot& h, const DevDraw& d, const GradTable
   return composite_generic(d, T, prec, fmt, raw, mask, use_mask, x, y);
 }
 
+// composite_cov for a gradient / dither source sampled through a PatternSampler (gradient and stops staged in shared memory,
+// row-invariant offset arithmetic hoisted): same coverage -> mask rules, same operator arithmetic as composite_generic.
+Z2D_D uint32_t composite_cov_pattern(const DrawHot& h, const PatternSampler& ps, const TileFmt& tf, uint32_t raw, int cov, int x, int y) {
+  const uint32_t fmt = tf.fmt;
+  int mask;
+  bool use_mask;
+  if (h.aa == Z2D_AA_SUPERSAMPLE_4X) {
+    if (fmt == Z2D_FMT_ALPHA4 || fmt == Z2D_FMT_ALPHA2 || fmt == Z2D_FMT_ALPHA1) {
+      const int bits = fmt_bits(fmt);
+      mask = scale_alpha((((1 << bits) - 1) * cov) / 16, bits, 8);
+    } else {
+      mask = (255 * cov) / 16;
+    }
+    use_mask = true;
+  } else {
+    if (cov == 0) return raw;
+    if (h.op == Z2D_OP_CLEAR) return 0u;
+    if (h.aa == Z2D_AA_NONE || cov == 16) {
+      mask = 255;
+      use_mask = false;
+    } else {
+      mask = 16 * cov - 1;
+      use_mask = true;
+    }
+  }
+  if (h.precision == Z2D_PRECISION_INTEGER) {
+    RGBA16 s = tf.is32 ? ps.sample_int<false>(x, y) : ps.sample_int<true>(x, y);  // (alpha formats keep nothing but alpha)
+    if (use_mask) s = mask_mul16(s, mask);
+    return tf_pack(tf, int_op_sw(h.op, tf_unpack(tf, raw), s));
+  }
+  RGBAF s = tf.is32 ? ps.sample_float<false>(x, y) : ps.sample_float<true>(x, y);
+  if (use_mask) {
+    const float ma = (float)mask / 255.0f;
+    s = {s.r * ma, s.g * ma, s.b * ma, ma * s.a};
+  }
+  return tf_pack(tf, encode_raw(float_op(h.op, decode_raw(tf_unpack(tf, raw)), s)));
+}
+
 // ------------------------------------------------------------------------- coverage
 template <int W>
 Z2D_D void wind_add(uint64_t (&p)[W], uint64_t mask, bool up) {
@@ -372,39 +410,13 @@ Z2D_D void cross_pass32(const uint4* __restrict__ es, uint32_t my0, uint32_t my1
   if (TWO) m1 = b;
 }
 
+// Second half of tile_cover32 / tile_cover_big: the difference array is complete (every lane's atomics issued), `cross` / `up`
+// say whether this lane's slot holds a crossing edge and its direction.
 template <bool TWO>
-Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, int sx0,
-                        uint32_t rule, uint2* __restrict__ diff, uint4* __restrict__ es, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
-  constexpr int ncols = TWO ? 64 : 16, nrows = TWO ? 64 : 16;
-  const bool even_odd = rule == Z2D_FILL_EVEN_ODD;
+Z2D_D void tile_cover_tail(const uint4* __restrict__ es, uint2* __restrict__ diff, bool cross, bool up, int ys0, int sx0, bool even_odd,
+                           uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
+  constexpr int ncols = TWO ? 64 : 16;
   const int lane = (int)(threadIdx.x & 31u);
-  const int sx_hi = sx0 + ncols;
-  reinterpret_cast<uint4*>(diff)[lane] = make_uint4(0u, 0u, 0u, 0u);  // entries 0 .. 65
-  if (lane == 0) reinterpret_cast<uint4*>(diff)[32] = make_uint4(0u, 0u, 0u, 0u);
-  bool cross = false, up = false;
-  __syncwarp();
-  if ((uint32_t)lane < n_be) {
-    const int4 h = __ldg(hd + lane);
-    {  // the edge itself goes to shared memory now (coalesced, independent of the header): the crossing pass gathers from there
-      const uint4* g = reinterpret_cast<const uint4*>(be + lane);
-      const uint4 e0 = __ldg(g), e1 = __ldg(g + 1);
-      es[lane] = e0;
-      es[32 + lane] = e1;
-    }
-    const int r0 = max((h.z & 0x7fffffff) - ys_tile0, 0), r1 = min(h.w - ys_tile0, nrows - 1);
-    up = h.z < 0;
-    if (h.x <= sx_hi && r0 <= r1) {  // else entirely right of the tile, or not active on its rows
-      if (h.y < sx0) {               // entirely left: only its winding matters
-        const int dir = up ? 1 : -1;
-        atomicAdd(reinterpret_cast<int*>(&diff[r0].x), dir);
-        atomicAdd(reinterpret_cast<int*>(&diff[r1 + 1].x), -dir);
-      } else {
-        cross = true;
-        atomicXor(&diff[r0].y, 1u << lane);
-        atomicXor(&diff[r1 + 1].y, 1u << lane);
-      }
-    }
-  }
   const uint32_t cross_b = __ballot_sync(0xffffffffu, cross), up_b = __ballot_sync(0xffffffffu, up);
   __syncwarp();
   int wl0, wl1 = 0;
@@ -463,11 +475,97 @@ Z2D_D void tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__
     if (TWO) cross_pass32<5, false>(es, my1, 0u, up_b, ys0 + 1, sx0, ncols, false, b1, 0, m1, dummy, n_eval);
   } else {  // (at most 32 crossing edges here: 8 planes hold +-64)
     uint64_t dummy = 0;
-    cross_pass<8, false>(be, hd, n_be, (uint64_t)cross_b, ys0, sx0, ncols, false, b0, 0, m0, dummy, n_eval);
-    if (TWO) cross_pass<8, false>(be, hd, n_be, (uint64_t)cross_b, ys0 + 1, sx0, ncols, false, b1, 0, m1, dummy, n_eval);
+    cross_pass32<8, false>(es, my0, 0u, up_b, ys0, sx0, ncols, false, b0, 0, m0, dummy, n_eval);
+    if (TWO) cross_pass32<8, false>(es, my1, 0u, up_b, ys0 + 1, sx0, ncols, false, b1, 0, m1, dummy, n_eval);
   }
   if (full0) m0 = ~0ull;
   if (full1) m1 = ~0ull;
+}
+
+// BIG = false: n_be <= 32, lane j holds edge j.
+// BIG = true (RICH kernel): also n_be > 32 -- strokes with round joins and caps bin dozens of short edges per tile row, most of
+// them elsewhere along x: lanes stride over the headers, edges left of the tile go straight into the winding differences and
+// the crossing ones are compacted into the 32 shared-memory slots, so that the rest runs exactly as in the small case (ONE copy
+// of the tail: a second one cost the stroke workload 30 %).  Returns false only when more than 32 edges cross the tile.
+template <bool TWO, bool BIG>
+Z2D_D bool tile_cover32(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys_tile0, int ys0, int sx0,
+                        uint32_t rule, uint2* __restrict__ diff, uint4* __restrict__ es, uint32_t* __restrict__ meta, uint64_t& m0, uint64_t& m1,
+                        uint32_t& n_eval) {
+  constexpr int ncols = TWO ? 64 : 16, nrows = TWO ? 64 : 16;
+  const int lane = (int)(threadIdx.x & 31u);
+  const int sx_hi = sx0 + ncols;
+  reinterpret_cast<uint4*>(diff)[lane] = make_uint4(0u, 0u, 0u, 0u);  // entries 0 .. 65
+  if (lane == 0) reinterpret_cast<uint4*>(diff)[32] = make_uint4(0u, 0u, 0u, 0u);
+  bool cross = false, up = false;
+  __syncwarp();
+  if (!BIG || n_be <= 32u) {
+    if ((uint32_t)lane < n_be) {
+      const int4 h = __ldg(hd + lane);
+      {  // the edge itself goes to shared memory now (coalesced, independent of the header): the crossing pass gathers from there
+        const uint4* g = reinterpret_cast<const uint4*>(be + lane);
+        const uint4 e0 = __ldg(g), e1 = __ldg(g + 1);
+        es[lane] = e0;
+        es[32 + lane] = e1;
+      }
+      const int r0 = max((h.z & 0x7fffffff) - ys_tile0, 0), r1 = min(h.w - ys_tile0, nrows - 1);
+      up = h.z < 0;
+      if (h.x <= sx_hi && r0 <= r1) {  // else entirely right of the tile, or not active on its rows
+        if (h.y < sx0) {               // entirely left: only its winding matters
+          const int dir = up ? 1 : -1;
+          atomicAdd(reinterpret_cast<int*>(&diff[r0].x), dir);
+          atomicAdd(reinterpret_cast<int*>(&diff[r1 + 1].x), -dir);
+        } else {
+          cross = true;
+          atomicXor(&diff[r0].y, 1u << lane);
+          atomicXor(&diff[r1 + 1].y, 1u << lane);
+        }
+      }
+    }
+  } else {
+    uint32_t n_slots = 0;
+    for (uint32_t base = 0; base < n_be; base += 32) {
+      const uint32_t i = base + (uint32_t)lane;
+      bool c = false, u = false;
+      int r0 = 0, r1 = 0;
+      if (i < n_be) {
+        const int4 h = __ldg(hd + i);
+        r0 = max((h.z & 0x7fffffff) - ys_tile0, 0);
+        r1 = min(h.w - ys_tile0, nrows - 1);
+        u = h.z < 0;
+        if (h.x <= sx_hi && r0 <= r1) {
+          if (h.y < sx0) {
+            const int dir = u ? 1 : -1;
+            atomicAdd(reinterpret_cast<int*>(&diff[r0].x), dir);
+            atomicAdd(reinterpret_cast<int*>(&diff[r1 + 1].x), -dir);
+          } else {
+            c = true;
+          }
+        }
+      }
+      const uint32_t cb = __ballot_sync(0xffffffffu, c);
+      if (c) {
+        const uint32_t slot = n_slots + (uint32_t)__popc(cb & ((1u << lane) - 1u));
+        if (slot < 32u) {
+          const uint4* g = reinterpret_cast<const uint4*>(be + i);
+          es[slot] = __ldg(g);
+          es[32 + slot] = __ldg(g + 1);
+          meta[slot] = (uint32_t)r0 | ((uint32_t)(r1 + 1) << 8) | (u ? 0x10000u : 0u);
+        }
+      }
+      n_slots += (uint32_t)__popc(cb);
+    }
+    if (n_slots > 32u) return false;
+    __syncwarp();
+    if ((uint32_t)lane < n_slots) {
+      const uint32_t mt = meta[lane];
+      cross = true;
+      up = (mt & 0x10000u) != 0u;
+      atomicXor(&diff[mt & 0xffu].y, 1u << lane);
+      atomicXor(&diff[(mt >> 8) & 0xffu].y, 1u << lane);
+    }
+  }
+  tile_cover_tail<TWO>(es, diff, cross, up, ys0, sx0, rule == Z2D_FILL_EVEN_ODD, m0, m1, n_eval);
+  return true;
 }
 
 // Draws flagged kDrawUnpaired only.  The reference pairs the sorted (filtered) crossings of a scanline and drops a
@@ -547,17 +645,80 @@ Z2D_D void blend_fast8(uint4& v0, uint4& v1, uint32_t cov_e, uint32_t cov_o, con
 }
 Z2D_D uint32_t nonzero_bytes(uint32_t x) { return (uint32_t)__popc(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu | x) & 0x80808080u); }
 
-// One warp per tile.  The default is ONE WARP PER CTA (32 threads, 32 CTAs per SM at 64 registers): everything derived from
-// blockIdx is then uniform for the compiler (uniform registers and datapath instead of one copy per lane), which measured
-// 3.03 ms against 3.34 ms (128 threads) and 3.9 ms (256 threads) on the 100 k-path scene.
+// Gradient / dither source on one (draw, tile) pair: a real function (values and plain pointers only), so that its registers --
+// the f64 row terms of the offset arithmetic, the 28-operator float pipeline -- do not weigh on the allocation of the kernel's hot
+// path.  Stages the gradient, its stops and the source record in shared memory once per pair and samples with the row-invariant
+// part of the offset arithmetic hoisted (a lane's 8 pixels share a row).  Returns the number of pixels composited by this lane.
+// flags: 1 unbounded MSAA pre-clear, 2 every pixel of the region is composited (supersample), 4 the lane's row is on the surface.
+__device__ __noinline__ uint32_t pattern_tile(const DevDraw* dp, const DrawHot* hp, GradTables T, uint32_t* px, DevGrad* sg, float* soff,
+                                              float4* scol, DevSrc* psrc, uint32_t cov_e, uint32_t cov_o, int px0, int py, int sfc_w,
+                                              uint32_t fmt, uint32_t flags) {
+  const int lane = (int)(threadIdx.x & 31u);
+  const DrawHot& h = *hp;
+  const bool pre = (flags & 1u) != 0u, all_px = (flags & 2u) != 0u, row_ok = (flags & 4u) != 0u;
+  TileFmt tf;
+  tf.fmt = fmt;
+  tf.is32 = fmt <= Z2D_FMT_RGBA;
+  tf.f = fmt32_of(fmt);
+  {
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&dp->src);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(psrc);
+    for (int k = lane; k < (int)(sizeof(DevSrc) / 4); k += 32) sw[k] = gw[k];
+  }
+  const GradTables Tp = pattern_stage(dp->src, T, sg, soff, scol, lane, 32);
+  __syncwarp();
+  PatternSampler ps;
+  ps.init(psrc, sg, Tp);
+  ps.set_row(py);
+  uint32_t n_cov = 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    const int x = px0 + i;
+    const int cov = (int)(((i & 1) ? cov_o : cov_e) >> (8 * (i >> 1))) & 0xff;
+    const bool in_sfc = x < sfc_w && row_ok;
+    const bool in_reg = in_sfc && x >= h.rx0 && x < h.rx1 && py >= h.ry0 && py < h.ry1;
+    if (!(in_sfc && (pre || (in_reg && (all_px || cov != 0))))) continue;
+    const int pi = (((i) >> 2) << 7) + (lane << 2) + ((i) & 3);
+    uint32_t raw = px[pi];
+    if (pre) {  // multisample.zig:96-110
+      if (py < h.pre_y0 || (py > h.pre_y1 && py < h.pre_rows) || (py >= h.pre_y0 && py <= h.pre_y1 && x < h.pre_x)) raw = 0u;
+    }
+    if (in_reg) {
+      n_cov += cov > 0;
+      raw = composite_cov_pattern(h, ps, tf, raw, cov, x, py);
+    }
+    px[pi] = raw;
+  }
+  __syncwarp();
+  return n_cov;
+}
+
+// One warp per tile.  The default is ONE WARP PER CTA (32 threads): everything derived from blockIdx is then uniform for the
+// compiler (uniform registers and datapath instead of one copy per lane), which measured 3.03 ms against 3.34 ms (128 threads)
+// and 3.9 ms (256 threads) on the 100 k-path scene.
+// Two instantiations, because the hot path is sensitive to everything that shares its register allocation:
+//   LEAN  batches of fills with single-pixel sources (config 2): 64 registers, 32 CTAs per SM;
+//   RICH  batches with strokes or gradient / dither sources: adds the compaction of crossing edges for tile rows with more
+//         than 32 binned edges (tile_cover_big) and the staged pattern path (pattern_tile); 80 registers, 24 CTAs per SM.
+//   Same box, raster ms (config 2 / config 3 / 256 config-5 scenes): LEAN-only code 2.37 / 10.8 / 10.4, RICH code for
+//   everything 2.69 / 7.5 / 8.6.
 #ifndef Z2D_RASTER_MIN_CTAS
 #define Z2D_RASTER_MIN_CTAS (2048 / Z2D_RASTER_THREADS > 32 ? 32 : 2048 / Z2D_RASTER_THREADS)
 #endif
-__global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(RasterArgs A) {
+#ifndef Z2D_RASTER_RICH_MIN_CTAS
+#define Z2D_RASTER_RICH_MIN_CTAS (Z2D_RASTER_MIN_CTAS * 3 / 4)
+#endif
+template <bool RICH>
+Z2D_D void raster_tiles_body(const RasterArgs& A) {
   __shared__ __align__(16) uint32_t tile_px[kRasterThreads / 32][8 * 32];
   __shared__ uint4 blend_tab[kRasterThreads / 32][17];
   __shared__ __align__(16) uint2 diff_s[kRasterThreads / 32][66];  // per warp: row difference array of tile_cover32 (int[132] view: tile_cover)
-  __shared__ __align__(16) uint4 edge_s[kRasterThreads / 32][2][32];  // per warp: the (<= 32) binned edges of the current pair
+  __shared__ __align__(16) uint4 edge_s[kRasterThreads / 32][2][32];  // per warp: the (<= 32) crossing edges of the current pair
+  __shared__ uint32_t meta_s[kRasterThreads / 32][32];
+  __shared__ __align__(16) DevGrad grad_s[kRasterThreads / 32];      // per warp: gradient / stops / source of the current pattern draw
+  __shared__ float soff_s[kRasterThreads / 32][kGenMaxStops];
+  __shared__ float4 scol_s[kRasterThreads / 32][kGenMaxStops];
+  __shared__ DevSrc psrc_s[kRasterThreads / 32];                // per warp: row range | direction of compacted crossing edges
   const int warp = kRasterThreads == 32 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
   if (gt >= A.n_tiles) return;
@@ -637,8 +798,9 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         uint64_t m0 = 0, m1 = 0;
         if (aa != Z2D_AA_NONE) {
           const int sx0 = tx * kTile * 4;
-          if (nbe <= 32u) tile_cover32<true>(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, sx0, rule, diff_s[warp], edge_s[warp][0], m0, m1, n_eval);
-          else tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
+          if ((!RICH && nbe > 32u) ||
+              !tile_cover32<true, RICH>(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, sx0, rule, diff_s[warp], edge_s[warp][0], meta_s[warp], m0, m1, n_eval))
+            tile_cover(be, hd, nbe, ty * kTile * 4, ty * kTile * 4 + lane * 2, true, sx0, 64, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
           if (unpaired) {
             m0 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2, sx0, 64, m0);
             m1 = cut_open_tail(A, h, ty * kTile * 4 + lane * 2 + 1, sx0, 64, m1);
@@ -652,8 +814,9 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
           cov_o = ((a >> 4) & 0x0f0f0f0fu) + ((b >> 4) & 0x0f0f0f0fu) + ((c >> 4) & 0x0f0f0f0fu) + ((e2 >> 4) & 0x0f0f0f0fu);
         } else {
           const int sx0 = tx * kTile;
-          if (nbe <= 32u) tile_cover32<false>(be, hd, nbe, ty * kTile, ty * kTile + row, sx0, rule, diff_s[warp], edge_s[warp][0], m0, m1, n_eval);
-          else tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
+          if ((!RICH && nbe > 32u) ||
+              !tile_cover32<false, RICH>(be, hd, nbe, ty * kTile, ty * kTile + row, sx0, rule, diff_s[warp], edge_s[warp][0], meta_s[warp], m0, m1, n_eval))
+            tile_cover(be, hd, nbe, ty * kTile, ty * kTile + row, false, sx0, 16, rule, reinterpret_cast<int*>(diff_s[warp]), m0, m1, n_eval);
           if (unpaired) m0 = cut_open_tail(A, h, ty * kTile + row, sx0, 16, m0);
           const uint32_t bits = ((uint32_t)m0 >> (half * 8)) & 0xffu;
           for (int i = 0; i < 8; i += 2) {
@@ -739,6 +902,13 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
         continue;
       }
       const DevDraw& d = A.draws[di];
+      if (RICH && (d.src.kind == Z2D_PARAM_GRADIENT || d.src.kind == Z2D_PARAM_DITHER) &&
+          (!(d.src.kind == Z2D_PARAM_GRADIENT || d.src.dither_source == Z2D_DITHER_SRC_GRADIENT) || A.T.grads[d.src.grad].n_stops <= (uint32_t)kGenMaxStops)) {
+        n_cov += pattern_tile(&d, &h, A.T, px, &grad_s[warp], soff_s[warp], scol_s[warp], &psrc_s[warp], cov_e, cov_o, px0, py, S.w, S.fmt,
+                              (pre ? 1u : 0u) | (all_px ? 2u : 0u) | (row_ok ? 4u : 0u));
+        dirty = true;
+        continue;
+      }
 #pragma unroll 1  // one copy of the generic compositor (28 operators x sources x formats) instead of eight
       for (int i = 0; i < 8; i++) {
         const int x = px0 + i;
@@ -783,6 +953,11 @@ __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_
       if (n_eval) atomicAdd(&A.counters[3], (unsigned long long)n_eval);
     }
   }
+}
+
+__global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(const __grid_constant__ RasterArgs A) { raster_tiles_body<false>(A); }
+__global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_RICH_MIN_CTAS) k_raster_tiles_rich(const __grid_constant__ RasterArgs A) {
+  raster_tiles_body<true>(A);
 }
 
 }  // namespace z2d

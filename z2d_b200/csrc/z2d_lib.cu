@@ -92,7 +92,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0, n_srcs = 0;
   int set = 0;  // which InputSet holds the batch
   size_t n_nodes = 0, h2d_bytes = 0;
 };
@@ -635,7 +635,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.counters = c->d_counters.as<unsigned long long>();
   A.sim_rows = c->d_sim_rows.as<int4>();
   A.T = tables(c, S.grads, S.stop_off, S.stop_col);
-  launch_raster(A, st);
+  launch_raster(A, m.n_strokes != 0 || m.n_srcs != 0, st);
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev[4], st));
   launches += 9;
@@ -792,6 +792,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.n_sp = n_sp;
   m.n_par_sp = B.n_par_sp;
   m.n_strokes = (uint32_t)B.strokes.size();
+  m.n_srcs = (uint32_t)B.srcs.size();
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
   m.n_work = n_work;
