@@ -214,6 +214,19 @@ int32_t z2d_surface_create(z2d_ctx* ctx, uint32_t format, int32_t width, int32_t
 int32_t z2d_surface_create_band(z2d_ctx* ctx, uint32_t format, int32_t width, int32_t canvas_height, int32_t band_y0,
                                 int32_t band_rows, const z2d_pixel* initial_px, z2d_sfc** out);
 int32_t z2d_surface_band(const z2d_sfc* sfc, int32_t* band_y0, int32_t* canvas_height);
+/* Band VIEWS: the band's rows live inside a full canvas instead of a buffer of their own, so a finished band IS its part of
+ * the canvas and the "gather bands to one rank" step of SURVEY 8e disappears into the raster kernel's tile write-back.
+ *   z2d_surface_band_view       band over a canvas of the same context (rank 0's own band);
+ *   z2d_surface_ipc_export      64-byte CUDA IPC handle of a canvas, to be sent to the other ranks of the node (any host channel);
+ *   z2d_surface_open_peer_band  band over a canvas that lives on ANOTHER process / GPU of the node: tile loads and the one
+ *                               write-back per touched tile go over NVLink (peer mapping) straight into that canvas.
+ * The owner of the canvas reads it after the writers have synchronised (z2d_sync on every rank, then a host barrier).  For the
+ * packed formats a band must start on a 16-byte boundary of the canvas.  The views do not own the pixels: destroy them before
+ * the canvas.  (No reference counterpart: z2d is single-process; the seam is Surface.buf being a slice of a larger buffer.) */
+int32_t z2d_surface_band_view(z2d_sfc* canvas, int32_t band_y0, int32_t band_rows, z2d_sfc** out);
+int32_t z2d_surface_ipc_export(z2d_sfc* canvas, void* handle64);
+int32_t z2d_surface_open_peer_band(z2d_ctx* ctx, const void* handle64, uint32_t format, int32_t width, int32_t canvas_height,
+                                   int32_t band_y0, int32_t band_rows, z2d_sfc** out);
 void z2d_surface_destroy(z2d_sfc* sfc);
 size_t z2d_surface_byte_len(const z2d_sfc* sfc);
 int32_t z2d_surface_width(const z2d_sfc* sfc);

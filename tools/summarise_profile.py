@@ -28,7 +28,7 @@ for r in rows[1:]:
     a[1] += v
     a[2] = max(a[2], v)
 total = sum(a[1] for a in agg.values())
-out = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --chunk 0",
+out = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c5 --chunk 0",
        "note": "per-launch times under ncu are serialised and cold-cache; the SHARE of each kernel is what carries over to the bench",
        "total_ms": total / 1e6,
        "kernels": [{"kernel": k, "launches": a[0], "total_ms": a[1] / 1e6, "max_ms": a[2] / 1e6, "share": a[1] / total}
@@ -45,7 +45,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "smsp__sass_inst_executed_op_local_ld.sum",
         "smsp__sass_inst_executed_op_local_st.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed"]
-for kern in ("raster", "flatten", "composite"):
+for kern in ("raster", "flatten", "composite", "raster_strokes", "flatten_strokes", "composite_gen", "composite_lut"):
     try:
         rows = list(csv.reader(open(G + f"{kern}_raw.csv")))
     except FileNotFoundError:

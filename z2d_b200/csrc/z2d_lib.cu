@@ -88,6 +88,9 @@ struct z2d_sfc {
   size_t bytes;
   int32_t slot[2];  // index in the surface table of recording batch 0 / 1, or -1
   int32_t y0 = 0, vh = 0;  // band surface: rows [y0, y0 + h) of a canvas vh rows high (ordinary surface: 0, h)
+  // band VIEW: `data` points into another surface's memory -- a canvas of this process (parent) or of a peer process (IPC)
+  bool external = false;
+  void* ipc_base = nullptr;  // cudaIpcOpenMemHandle mapping to close
 };
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
@@ -1224,8 +1227,71 @@ void z2d_surface_destroy(z2d_sfc* s) {
     cudaStreamSynchronize(c->d2h_stream);
     c->d2h_pending = false;
   }
-  cudaFree(s->data);
+  if (s->ipc_base) cudaIpcCloseMemHandle(s->ipc_base);
+  else if (!s->external) cudaFree(s->data);
   delete s;
+}
+
+// ---- band views: the band's rows live INSIDE a full canvas, so finishing a band is finishing its part of the canvas.  With
+// the canvas on another GPU of the node (IPC handle, NVLink peer mapping) the raster kernel's tile loads and its one
+// write-back per touched tile go straight over NVLink into rank 0's canvas: the gather of SURVEY 8e is fused into K4's
+// write-back, there is no separate copy or collective to wait for.
+static int32_t make_band_view(z2d_ctx* c, uint8_t* base, void* ipc_base, uint32_t format, int32_t width, int32_t canvas_height, int32_t band_y0,
+                              int32_t band_rows, z2d_sfc** out) {
+  if (!c || !out || format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
+  *out = nullptr;
+  if (width < 1) return Z2D_E_INVALID_WIDTH;
+  if (canvas_height < 1) return Z2D_E_INVALID_HEIGHT;
+  if (band_y0 < 0 || band_rows < 1 || (band_y0 & (kTile - 1)) != 0 || band_y0 + band_rows > canvas_height) return Z2D_E_INVALID_ARG;
+  const size_t bit0 = (size_t)band_y0 * (size_t)width * (size_t)fmt_bits(format);
+  const size_t bits = (size_t)band_rows * (size_t)width * (size_t)fmt_bits(format);
+  // packed formats: a band must start and end on a byte (16 bytes for the vector paths) so that no byte is shared with a neighbour band
+  if ((bit0 & 127) != 0 || ((bits & 7) != 0 && band_y0 + band_rows != canvas_height)) return Z2D_E_INVALID_ARG;
+  z2d_sfc* s = new z2d_sfc();
+  s->ctx = c;
+  s->fmt = format;
+  s->w = width;
+  s->h = band_rows;
+  s->y0 = band_y0;
+  s->vh = canvas_height;
+  s->bytes = (bits + 7) / 8;
+  s->slot[0] = s->slot[1] = -1;
+  s->data = base + bit0 / 8;
+  s->external = true;
+  s->ipc_base = ipc_base;
+  *out = s;
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_band_view(z2d_sfc* canvas, int32_t band_y0, int32_t band_rows, z2d_sfc** out) {
+  if (!canvas || canvas->external || canvas->y0 != 0 || canvas->vh != canvas->h) return Z2D_E_INVALID_ARG;
+  return make_band_view(canvas->ctx, canvas->data, nullptr, canvas->fmt, canvas->w, canvas->h, band_y0, band_rows, out);
+}
+
+int32_t z2d_surface_ipc_export(z2d_sfc* s, void* handle64) {
+  if (!s || !handle64 || s->external) return Z2D_E_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));  // the memset / paint of the creation must have landed before a peer writes
+  CK(c, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), s->data));
+  return Z2D_OK;
+}
+
+int32_t z2d_surface_open_peer_band(z2d_ctx* c, const void* handle64, uint32_t format, int32_t width, int32_t canvas_height, int32_t band_y0,
+                                   int32_t band_rows, z2d_sfc** out) {
+  if (!c || !handle64 || !out) return Z2D_E_INVALID_ARG;
+  *out = nullptr;
+  cudaSetDevice(c->device);
+  void* base = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  CK(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  int32_t rc = make_band_view(c, (uint8_t*)base, base, format, width, canvas_height, band_y0, band_rows, out);
+  if (rc != Z2D_OK) cudaIpcCloseMemHandle(base);
+  return rc;
 }
 
 size_t z2d_surface_byte_len(const z2d_sfc* s) { return s ? s->bytes : 0; }

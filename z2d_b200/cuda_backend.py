@@ -41,6 +41,9 @@ def load_library():
         "z2d_surface_create": (C.c_int32, [vp, C.c_uint32, C.c_int32, C.c_int32, P(abi.PixelPOD), P(vp)]),
         "z2d_surface_create_band": (C.c_int32, [vp, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(abi.PixelPOD), P(vp)]),
         "z2d_surface_band": (C.c_int32, [vp, P(C.c_int32), P(C.c_int32)]),
+        "z2d_surface_band_view": (C.c_int32, [vp, C.c_int32, C.c_int32, P(vp)]),
+        "z2d_surface_ipc_export": (C.c_int32, [vp, vp]),
+        "z2d_surface_open_peer_band": (C.c_int32, [vp, vp, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(vp)]),
         "z2d_surface_destroy": (None, [vp]),
         "z2d_surface_byte_len": (C.c_size_t, [vp]),
         "z2d_surface_width": (C.c_int32, [vp]),
@@ -70,7 +73,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
-                    "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_destroy", "z2d_surface_byte_len",
+                    "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_band_view", "z2d_surface_ipc_export", "z2d_surface_open_peer_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
                     "z2d_surface_download", "z2d_surface_download_async", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel",
                     "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
@@ -111,6 +114,21 @@ class CudaBackend:
         out = C.c_void_p()
         px = C.byref(initial_px.pod()) if initial_px is not None else None
         self._check(self.lib.z2d_surface_create_band(self.ctx, int(fmt), w, canvas_h, y0, rows, px, C.byref(out)))
+        return out
+
+    def surface_band_view(self, canvas_hd, y0, rows):
+        out = C.c_void_p()
+        self._check(self.lib.z2d_surface_band_view(canvas_hd, y0, rows, C.byref(out)))
+        return out
+
+    def surface_ipc_export(self, canvas_hd):
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.z2d_surface_ipc_export(canvas_hd, buf))
+        return buf.raw
+
+    def surface_open_peer_band(self, handle, fmt, w, canvas_h, y0, rows):
+        out = C.c_void_p()
+        self._check(self.lib.z2d_surface_open_peer_band(self.ctx, C.create_string_buffer(handle, 64), int(fmt), w, canvas_h, y0, rows, C.byref(out)))
         return out
 
     def surface_destroy(self, hd):

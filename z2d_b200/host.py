@@ -568,6 +568,27 @@ class Surface:
             self.band_y0, self.height = int(band[0]), int(band[1])
             self.handle = self.backend.surface_create_band(self.format, self.width, self.canvas_height, self.band_y0, self.height, initial_px)
 
+    @classmethod
+    def _wrap(cls, backend, handle, format, width, canvas_height, y0, rows):
+        s = cls.__new__(cls)
+        s.backend, s.format, s.width, s.canvas_height = backend, Format(format), int(width), int(canvas_height)
+        s.band_y0, s.height, s.handle = int(y0), int(rows), handle
+        return s
+
+    def band_view(self, y0, rows):
+        """Rows [y0, y0 + rows) of this canvas as a band surface over the SAME memory (z2d_surface_band_view)."""
+        return Surface._wrap(self.backend, self.backend.surface_band_view(self.handle, int(y0), int(rows)), self.format, self.width, self.height, y0, rows)
+
+    def ipc_export(self):
+        """64-byte handle another process of the node opens with Surface.open_peer_band (z2d_surface_ipc_export)."""
+        return self.backend.surface_ipc_export(self.handle)
+
+    @staticmethod
+    def open_peer_band(handle, format, width, canvas_height, y0, rows, backend=None):
+        """Band over a canvas that lives on another process / GPU of the node: writes go over NVLink into that canvas."""
+        backend = backend or default_backend()
+        return Surface._wrap(backend, backend.surface_open_peer_band(handle, format, width, canvas_height, y0, rows), format, width, canvas_height, y0, rows)
+
     @staticmethod
     def init(format, width, height, backend=None):
         return Surface(format, width, height, None, backend)
