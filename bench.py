@@ -153,6 +153,24 @@ def zig_probe():
         return f"zig probe failed: {e}"
 
 
+def pin_rank_cores(local_rank):
+    """Give every rank of a torchrun launch its own contiguous slice of the host cores this job may use (r01: with 8 ranks on one
+    32-core affinity mask the recorder threads and the read-backs of different ranks kept migrating over each other)."""
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    if local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    avail = sorted(os.sched_getaffinity(0))
+    per = len(avail) // local_world
+    if per < 2:
+        return None
+    mine = avail[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return [mine[0], mine[-1]]
+
+
 def canvas_scene(args, rank):
     """The ordered single-canvas workloads: config 2 (fills) and config 3 (strokes)."""
     from z2d_b200 import sharding, workloads
@@ -227,6 +245,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cores = pin_rank_cores(local_rank)  # before the context: the library sizes its recorder from the affinity mask
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     cb = CudaBackend(local_rank, stream=stream.cuda_stream)
@@ -252,6 +271,18 @@ def run_ours(args, rank, world, local_rank):
                     "roofline": {"kernel": "k_composite_fast", "bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
                                  "peak_kind": kind, "traffic": ncu_traffic("composite")[0]},
                     "c4_summary": bench_extra.c4_summary(cells), "c4_context_fill": rect, "c4_cells": cells, "gpu_launches": len(cells) * 4}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    if args.workload == "band":
+        b = bench_extra.run_band(cb, rank, world, ddist, args.band_size, args.paths, max(1, min(args.steps, 10)), 2, verify=args.verify)
+        if rank == 0:
+            line = {"metric": "band canvas Mpix/s (canvas pixels)", "value": b["canvas_mpix_s"], "unit": "Mpix/s", "n_gpus": world, "steps": b["steps"],
+                    "warmup": 2, "ms_per_step": b["ms_per_canvas"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                    "data": "synthetic", "config": {"workload": b["workload"]}, "band": b, "gpu_launches": 30 * b["steps"]}
             print(json.dumps(line), flush=True)
         if world > 1:
             dist.barrier()
@@ -385,6 +416,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "paths_per_s": draws_all * steps / (dev_ms * 1e-3),
             "config": {"workload": desc,
+                       "host_cores_rank0": cores,
                        "parallelism": f"independent scenes, 1 per GPU x{world} (no data-path collective); the sharded configuration (config 5, "
                                       "scene s -> rank s mod N, strong scaling) is the `c5` block of this line",
                        "value_definition": "inputs (nodes, draw records) resident in HBM when the timed region starts (z2d_replay); the node upload "
@@ -455,7 +487,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "band"],
                     help="c2 (default): the headline line, with config 5 as its `c5` block; c3 / c4 / c5: that configuration as the line")
     ap.add_argument("--paths", type=int, default=100_000)
     ap.add_argument("--size", type=int, default=4096)
@@ -467,6 +499,8 @@ def main():
     ap.add_argument("--no-composite", action="store_true", help="skip the K5 roofline leg (profiling runs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 block of the default line (profiling runs)")
     ap.add_argument("--quick", action="store_true", help="c4: one operator per cell group")
+    ap.add_argument("--band-size", type=int, default=16384, help="band: canvas edge in pixels")
+    ap.add_argument("--verify", action="store_true", help="band: compare the stacked canvas with a single-GPU render")
     ap.add_argument("--chunk", type=int, default=-1, help="recorder chunk size for the e2e leg (-1: library default, 0: one batch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -297,3 +297,70 @@ def run_c5(cb, rank, world, dist, n_scenes, size, steps, warmup, with_cpu=False,
     if with_cpu:
         out["cpu_baseline"] = cpu_c5(n_scenes, size)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ band canvas
+def run_band(cb, rank, world, dist, size, n_paths, steps, warmup, verify=False):
+    """One very large canvas (second row): rank r renders rows [r*H/N, (r+1)*H/N) of an HxH RGBA8 canvas that lives
+    on rank 0.  Every rank records the SAME draw calls on a band VIEW of that canvas -- rank 0 over its own memory, the others
+    over a CUDA-IPC peer mapping -- so the raster kernel's tile write-back lands in rank 0's canvas over NVLink and there is no
+    separate gather.  Device-timed per canvas (max over ranks), strong scaling."""
+    import torch
+    H = size
+    rows = (H // world) & ~15
+    assert rows * world == H, "canvas height must split into bands of whole tile rows"
+    scene = workloads.cubic_paths_scene(n_paths, H, seed=0x7A326402, r_log2=(5.0, 9.0))
+    canvas = Surface(Format.rgba, H, H, None, cb) if rank == 0 else None
+    if world > 1:
+        obj = [canvas.ipc_export() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        band = canvas.band_view(0, rows) if rank == 0 else Surface.open_peer_band(obj[0], Format.rgba, H, H, rank * rows, rows, cb)
+    else:
+        band = canvas.band_view(0, rows)
+    cmds = scene.draw_cmds(band.handle)
+    P = C.POINTER(abi.DrawCmdPOD)
+    zero = Pixel.rgba(0, 0, 0, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        band.paint_pixel(zero)
+        cb.submit(cmds.ctypes.data_as(P), scene.n)
+        cb.flush()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    st = cb.stats()
+    (dev_ms, wall_ms), (covered,) = sharding.reduce_timing([ev0.elapsed_time(ev1), wall_ms], [st["covered_px"]], device="cuda", dist=dist)
+    out = None
+    if rank == 0:
+        out = {"workload": f"band canvas: {H}x{H} RGBA8 ({H * H * 4 / 2**30:.2f} GiB), {n_paths} cubic paths (r 32-512), one band of {rows} rows per GPU; "
+                           "all ranks replay the same calls, bands are views of rank 0's canvas (peer mapping over NVLink): the gather is K4's write-back",
+               "n_gpus": world, "steps": steps, "ms_per_canvas": dev_ms / steps, "wall_ms_per_canvas": wall_ms / steps, "scaling": "strong",
+               "canvas_mpix_s": H * H / (dev_ms / steps * 1e-3) / 1e6}
+        if verify:  # the stacked canvas equals a single-GPU render of the whole canvas
+            got = canvas.download().copy()
+            ref = Surface(Format.rgba, H, H, None, cb)
+            c2 = scene.draw_cmds(ref.handle)
+            cb.submit(c2.ctypes.data_as(P), scene.n)
+            out["equal_to_single_gpu_render"] = bool(np.array_equal(got, ref.download()))
+            ref.deinit()
+    if dist is not None:
+        dist.barrier()  # the peers keep their mappings until rank 0 has read the canvas
+    band.deinit()
+    if canvas is not None:
+        canvas.deinit()
+    return out

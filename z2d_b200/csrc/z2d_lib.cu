@@ -7,6 +7,8 @@
 // converting gradient stops to their interpolation space once per call
 // (the reference redoes that per pixel, color_vector.zig:197-207).
 #include <algorithm>
+#include <sched.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -989,6 +991,26 @@ int record_nodes(z2d_ctx* c, uint32_t draw_index, const z2d_node* nodes, size_t 
   return Z2D_OK;
 }
 
+// Band surfaces (one band per GPU of a very large canvas): every rank is handed the SAME calls, so a fill whose control-point
+// hull lies entirely above or below the rows this surface holds is dropped before it costs an upload and a flattening pass.
+// Exactly neutral: a curve stays inside the hull of its control points, so the fill has no edge -- hence no coverage region --
+// on these rows (only for bounded operators: the others also touch pixels outside the shape).
+bool fill_misses_band(const z2d_sfc* s, const z2d_node* nodes, size_t n, uint32_t op) {
+  if ((s->y0 == 0 && s->vh == s->h) || !op_is_bounded(op) || n == 0 || nodes[0].tag != Z2D_NODE_MOVE_TO) return false;
+  double lo = INFINITY, hi = -INFINITY;
+  for (size_t i = 0; i < n; i++) {
+    const z2d_node& nd = nodes[i];
+    const int np = nd.tag == Z2D_NODE_CURVE_TO ? 3 : (nd.tag == Z2D_NODE_CLOSE_PATH ? 0 : 1);
+    for (int k = 0; k < np; k++) {
+      const double y = nd.p[2 * k + 1];
+      if (!(y == y)) return false;  // NaN: leave it to the pipeline
+      lo = y < lo ? y : lo;
+      hi = y > hi ? y : hi;
+    }
+  }
+  return hi < (double)s->y0 - 2.0 || lo > (double)(s->y0 + s->h) + 2.0;
+}
+
 constexpr size_t kMaxBatchNodes = 8u << 20;   // flush thresholds (bounds pinned + device scratch)
 constexpr size_t kMaxBatchDraws = 1u << 20;
 constexpr size_t kMinChunkDraws = 8192;        // smallest batch worth handing to the worker (fixed cost of a batch ~0.3 ms)
@@ -1011,14 +1033,22 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   c->device = device;
   c->bat[1].index = 1;
   {
-    // share the host cores with the other ranks of a torchrun launch (LOCAL_WORLD_SIZE processes on this node): each rank
-    // already runs its caller, the batch worker and the CUDA driver threads, and with 8 ranks on 32 cores a second recording
-    // thread per rank measured 16.7 -> 19.2 ms per step end to end, so with several ranks a recording thread is added per eight cores a rank has
-    const unsigned hw = std::thread::hardware_concurrency();
+    // Recording threads for z2d_submit: from the cores this process may actually run on (its affinity mask -- a launcher that
+    // pins every rank to its own slice of the host is honoured), shared with the other ranks of a torchrun launch when nobody
+    // pinned anything (LOCAL_WORLD_SIZE processes on the same mask).  Two cores stay free for the caller and the batch worker.
+    unsigned avail = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    bool pinned = false;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+      const unsigned cnt = (unsigned)CPU_COUNT(&set);
+      pinned = cnt && cnt < avail;
+      if (cnt) avail = cnt;
+    }
     const char* env = getenv("Z2D_RECORD_THREADS");
     const char* lws = getenv("LOCAL_WORLD_SIZE");
-    const unsigned ranks = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
-    c->record_threads = env ? (unsigned)atoi(env) : std::min(4u, ranks > 1 ? hw / (8u * ranks) : hw / 2u);
+    const unsigned ranks = (!pinned && lws && atoi(lws) > 0) ? (unsigned)atoi(lws) : 1u;
+    const unsigned mine = avail / ranks;
+    c->record_threads = env ? (unsigned)atoi(env) : std::min(4u, mine > 2u ? mine - 2u : 1u);
     if (c->record_threads < 1) c->record_threads = 1;
   }
   if (stream) {
@@ -1514,6 +1544,7 @@ int32_t z2d_fill(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_n
   if (pattern->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(pattern->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;  // painter.zig:73-79
   if (n == 0) return Z2D_OK;                                         // painter.zig:81
   if (!is_closed_node_set(nodes, n)) return Z2D_E_PATH_NOT_CLOSED;   // painter.zig:82
+  if (fill_misses_band(s, nodes, n, o->op)) return Z2D_OK;
   DevDraw d;
   memset(&d, 0, sizeof d);
   d.kind = 0;
@@ -1668,6 +1699,10 @@ static void plan_fill(z2d_ctx* c, const z2d_draw_cmd& k, FillPlan& pl) {
   }
   if (!is_closed_node_set(k.nodes, k.n_nodes)) {
     pl.status = Z2D_E_PATH_NOT_CLOSED;
+    return;
+  }
+  if (fill_misses_band(s, k.nodes, k.n_nodes, o->op)) {
+    pl.skip = 1;
     return;
   }
   size_t first = 0;
