@@ -3,7 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA library)
   python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (rank 0 only)
-  python bench.py --workload c3|c4|c5 ...                  # config 3 (strokes) / config 4 (compositor sweep) / config 5 (scene batch)
+  python bench.py --workload c1|c3|c4|c5|band ...          # config 1 (logo latency) / 3 (strokes) / 4 (compositor sweep) / 5 (scene batch) / band canvas
 
 A *step* is one pass of the hot path over one batch: a zeroed 4096x4096 RGBA8
 canvas receives 100 000 ordered `painter.fill` calls (random closed 4-cubic
@@ -277,6 +277,19 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    if args.workload == "c1":
+        if rank == 0:
+            c1 = bench_extra.run_c1(cb, reps=max(100, args.steps * 30), with_cpu=not args.no_cpu_baseline)
+            line = {"metric": "scene latency", "value": c1["us_per_scene"], "unit": "us/scene", "n_gpus": 1, "steps": max(100, args.steps * 30), "warmup": 3,
+                    "ms_per_step": c1["us_per_scene"] / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                    "data": "spec/080 scene (reference test fonts)", "config": {"workload": c1["workload"]}, "c1": c1,
+                    "cpu_baseline": c1.get("cpu_baseline"), "gpu_launches": int(c1["kernel_launches_per_scene"])}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     if args.workload == "band":
         b = bench_extra.run_band(cb, rank, world, ddist, args.band_size, args.paths, max(1, min(args.steps, 10)), 2, verify=args.verify)
         if rank == 0:
@@ -487,7 +500,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "band"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "band"],
                     help="c2 (default): the headline line, with config 5 as its `c5` block; c3 / c4 / c5: that configuration as the line")
     ap.add_argument("--paths", type=int, default=100_000)
     ap.add_argument("--size", type=int, default=4096)

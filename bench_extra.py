@@ -364,3 +364,58 @@ def run_band(cb, rank, world, dist, size, n_paths, steps, warmup, verify=False):
     if canvas is not None:
         canvas.deinit()
     return out
+
+
+# ------------------------------------------------------------------------------------------------ config 1
+class _Recorder:
+    """Backend wrapper that records the (pattern, nodes, opts) of every fill so the scene can be replayed without text layout."""
+
+    def __init__(self, inner):
+        self.inner, self.calls = inner, []
+
+    def __getattr__(self, name):
+        return getattr(self.inner, name)
+
+    def fill(self, hd, pat, nodes, n, opts):
+        self.calls.append((pat, nodes, n, opts))
+        return self.inner.fill(hd, pat, nodes, n, opts)
+
+
+def _logo_loop(backend, reps, warm=3):
+    from tests import specs
+    from z2d_b200.abi import AntiAliasMode
+    rec = _Recorder(backend)
+    sfc = specs.PATH_SCENES["080_fill_z2d_logo"](specs.bind(rec), AntiAliasMode.default)
+    zero = Pixel.rgba(0, 0, 0, 0)
+
+    def scene():
+        sfc.paint_pixel(zero)
+        for pat, nodes, n, opts in rec.calls:
+            backend.fill(sfc.handle, pat, nodes, n, opts)
+        backend.sync()
+
+    for _ in range(warm):
+        scene()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        scene()
+    dt = time.perf_counter() - t0
+    return dt / reps * 1e6, sum(c[2] for c in rec.calls), len(rec.calls), sfc
+
+
+def run_c1(cb, reps=1000, with_cpu=True):
+    """BASELINE config 1 (spec/080_fill_z2d_logo): 601x172 RGBA8, five non-zero fills (3 polygons, 2 text runs), opaque source,
+    default AA.  Latency bound: timed as back-to-back scenes, each = clear + 5 painter.fill calls + wait for completion (glyph
+    outlines -> nodes is host-side text layout outside the path, so the node lists are built once)."""
+    gpu_us, nodes, calls, sfc = _logo_loop(cb, reps)
+    st = cb.stats()
+    out = {"workload": "BASELINE config 1: spec/080_fill_z2d_logo, 601x172 RGBA8, 5 fills (3 polygons + 2 text runs), opaque source, src_over, default AA; "
+                       "one scene = clear + 5 painter.fill + sync, node lists prebuilt",
+           "fills_per_scene": calls, "nodes_per_scene": nodes, "us_per_scene": gpu_us, "scenes_per_s": 1e6 / gpu_us, "paths_per_s": calls * 1e6 / gpu_us,
+           "bbox_mpix_s": st["region_px"] / gpu_us, "covered_mpix_s": st["covered_px"] / gpu_us, "kernel_launches_per_scene": st["kernel_launches"]}
+    if with_cpu:
+        from tests.oracle_backend import OracleBackend
+        cpu_us, _, _, _ = _logo_loop(OracleBackend(fast=True), 50)
+        out["cpu_baseline"] = {"value": cpu_us, "unit": "us/scene", "cores": 1, "kind": "port",
+                               "sample": "50 scenes; C++ restatement of z2d's CPU path (oracle/), not z2d itself"}
+    return out

@@ -255,6 +255,10 @@ int32_t z2d_surface_export(z2d_sfc* sfc, uint32_t flags, void* host, size_t n);
 /* Surface.paintPixel (surface.zig:295) */
 int32_t z2d_surface_paint_pixel(z2d_sfc* sfc, const z2d_pixel* px);
 /* Surface.putPixel (surface.zig:288): out-of-bounds coordinates are ignored */
+/* Surface.downsample (src/surface.zig:447-490, 687-709): 4x4 box average with truncation of every channel, in the surface's own
+ * format; width and height become width/4, height/4 (surfaces smaller than 4 pixels in either direction are left alone).  Whole
+ * surfaces only (not bands / views).  Flushes + syncs (the pixel buffer is replaced). */
+int32_t z2d_surface_downsample(z2d_sfc* sfc);
 int32_t z2d_surface_put_pixel(z2d_sfc* sfc, int32_t x, int32_t y, const z2d_pixel* px);
 /* Surface.getPixel (surface.zig:280): the pixel in the surface's own format (channel values as stored).  Returns 1 and leaves
  * *out untouched where the reference returns null (coordinates outside the surface, or outside the rows a band holds).

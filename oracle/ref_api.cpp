@@ -36,6 +36,22 @@ int32_t z2d_ref_surface_put_pixel(void* buf, uint32_t fmt, int32_t w, int32_t h,
   return Z2D_OK;
 }
 
+// Surface.downsample (surface.zig:447-490): in place; returns the new dimensions
+int32_t z2d_ref_surface_downsample(void* buf, uint32_t fmt, int32_t w, int32_t h, int32_t* w_out, int32_t* h_out) {
+  Sfc s{(uint8_t*)buf, fmt, w, h};
+  sfc_downsample(s);
+  *w_out = s.w;
+  *h_out = s.h;
+  return Z2D_OK;
+}
+
+// Polygon.inBox (Polygon.zig:142-201) on bare extents (the reference's own KAT table sets nothing else)
+int32_t z2d_ref_in_box(double left, double top, double right, double bottom, double scale, int32_t box_width, int32_t box_height) {
+  Polygon p;
+  p.ext_left = left; p.ext_top = top; p.ext_right = right; p.ext_bottom = bottom;
+  return p.in_box(scale, box_width, box_height) ? 1 : 0;
+}
+
 // benchmark statistic: pixels with coverage > 0 composited so far by the MSAA rasteriser
 uint64_t z2d_ref_covered_px(int32_t reset) {
   uint64_t v = g_covered_px;

@@ -92,6 +92,15 @@ class OracleBackend:
     def surface_paint_pixel(self, hd, px):
         abi.check(self.lib.z2d_ref_surface_paint_pixel(hd.ptr, hd.fmt, hd.w, hd.h, C.byref(px.pod())))
 
+    def surface_downsample(self, hd):
+        w, h = C.c_int32(), C.c_int32()
+        self.lib.z2d_ref_surface_downsample.restype = C.c_int32
+        self.lib.z2d_ref_surface_downsample.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        abi.check(self.lib.z2d_ref_surface_downsample(hd.ptr, hd.fmt, hd.w, hd.h, C.byref(w), C.byref(h)))
+        hd.w, hd.h = w.value, h.value
+        hd.buf = hd.buf[:abi.surface_byte_len(hd.fmt, hd.w, hd.h)].copy()
+        return hd.w, hd.h
+
     def surface_put_pixel(self, hd, x, y, px):
         abi.check(self.lib.z2d_ref_surface_put_pixel(hd.ptr, hd.fmt, hd.w, hd.h, x, y, C.byref(px.pod())))
 

@@ -10,7 +10,7 @@ import pytest
 from PIL import Image
 
 from tests import golden_util, specs
-from z2d_b200 import host
+from z2d_b200 import abi, host
 from z2d_b200.abi import AntiAliasMode, Format
 
 pytestmark = pytest.mark.gpu
@@ -137,3 +137,33 @@ def test_get_pixel_reads_what_the_surface_stores(cuda, fmt):
     again = sfc.get_pixel(4, 2)
     ref = sfc.get_pixel(13, 3)
     assert (again.r, again.g, again.b, again.a) == (ref.r, ref.g, ref.b, ref.a)
+
+
+@pytest.mark.parametrize("fmt", [Format.rgba, Format.argb, Format.rgb, Format.xrgb, Format.alpha8, Format.alpha4, Format.alpha2, Format.alpha1])
+def test_downsample_matches_reference_box_average(cuda, oracle, fmt):
+    """Surface.downsample (surface.zig:447-490, 687-709) as a standalone device call: every format, sizes that are not multiples
+    of 4 (the remainder rows / columns are dropped) and surfaces too small to downsample."""
+    from tests import specs
+    rng = np.random.default_rng(5)
+    for w, h in ((64, 32), (37, 23), (601, 172), (3, 9), (4, 4)):
+        data = rng.integers(0, 256, abi.surface_byte_len(fmt, w, h), dtype=np.uint8)
+        res = []
+        for z in (specs.bind(cuda), specs.bind(oracle)):
+            s = z.Surface(fmt, w, h)
+            s.upload(data.copy())
+            s.downsample()
+            res.append((s.get_width(), s.get_height(), s.download().copy()))
+        assert res[0][:2] == res[1][:2] == ((w // 4, h // 4) if w >= 4 and h >= 4 else (w, h))
+        a, b = res[0][2], res[1][2]
+        nbits = res[0][0] * res[0][1] * abi.FORMAT_BITS[fmt]
+        if nbits % 8:  # the last byte of a packed surface is only partly defined
+            a, b = a.copy(), b.copy()
+            m = (1 << (nbits % 8)) - 1
+            a[-1] &= m
+            b[-1] &= m
+        if fmt in (Format.rgb, Format.xrgb):
+            a, b = a.reshape(-1, 4).copy(), b.reshape(-1, 4).copy()
+            pad = 3 if fmt == Format.rgb else 3
+            a[:, pad] = 0
+            b[:, pad] = 0
+        assert np.array_equal(a, b), f"{fmt.name} {w}x{h}"

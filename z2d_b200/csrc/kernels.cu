@@ -1233,6 +1233,41 @@ void launch_export(const ExportArgs& A, int sm_count, cudaStream_t st) {
   k_export_rows<<<(unsigned)blocks, 256, 0, st>>>(A);
 }
 
+// Surface.downsample (surface.zig:447-469, 687-709): 4x4 box average with truncation, every format (`T.average`: the sum of the
+// 16 stored samples / 16 per channel; RGB / XRGB write padding 0).  Out of place (the reference compacts in place, sequentially:
+// same result, every output is written before the inputs of later outputs are reached).  One thread per output pixel.
+__global__ void k_downsample(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t fmt, int w_in, int w_out, int h_out) {
+  const size_t n = (size_t)w_out * (size_t)h_out;
+  const int bits = fmt_bits(fmt);
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+    const size_t y = o / (size_t)w_out, x = o - y * (size_t)w_out;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        const uint32_t raw = load_raw(src, fmt, (y * 4 + (size_t)i) * (size_t)w_in + (x * 4 + (size_t)j));
+        if (bits == 32) {
+          acc[0] += raw & 255u; acc[1] += (raw >> 8) & 255u; acc[2] += (raw >> 16) & 255u; acc[3] += raw >> 24;
+        } else {
+          acc[0] += raw;
+        }
+      }
+    uint32_t out;
+    if (bits == 32) {
+      out = (acc[0] / 16u) | ((acc[1] / 16u) << 8) | ((acc[2] / 16u) << 16) | ((acc[3] / 16u) << 24);
+      if (fmt == Z2D_FMT_RGB || fmt == Z2D_FMT_XRGB) out &= 0x00ffffffu;
+    } else {
+      out = acc[0] / 16u;
+    }
+    store_raw(dst, fmt, o, out);
+  }
+}
+void launch_downsample(const uint8_t* src, uint8_t* dst, uint32_t fmt, int w_in, int w_out, int h_out, cudaStream_t st) {
+  const size_t n = (size_t)w_out * (size_t)h_out;
+  if (!n) return;
+  unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148u * 16u);
+  k_downsample<<<blocks, 256, 0, st>>>(src, dst, fmt, w_in, w_out, h_out);
+}
+
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st) {
   unsigned blocks = (unsigned)((n_px + 255) / 256);
   if (blocks > 148u * 16u) blocks = 148u * 16u;

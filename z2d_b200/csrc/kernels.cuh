@@ -94,6 +94,7 @@ struct ExportArgs {  // z2d_surface_export
 };
 void launch_export(const ExportArgs& A, int sm_count, cudaStream_t st);
 void launch_paint(uint8_t* data, uint32_t fmt, size_t n_px, uint32_t raw, cudaStream_t st);
+void launch_downsample(const uint8_t* src, uint8_t* dst, uint32_t fmt, int w_in, int w_out, int h_out, cudaStream_t st);
 void launch_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t raw, cudaStream_t st);
 
 }  // namespace z2d

@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
+
 #include "blue_noise_table.h"
 #include "kernels.cuh"
 
@@ -197,6 +199,11 @@ struct z2d_ctx {
 };
 
 namespace {
+
+struct NvtxRange {  // host-side range around the launches of one pipeline stage (Nsight Systems timeline)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(z2d_ctx* c, const char* what, cudaError_t e) {
   if (c) {
@@ -520,6 +527,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     launches += 3;
     return cudaGetLastError();
   };
+  NvtxRange r_batch("z2d batch");
+  nvtxRangePushA("z2d K0-K1 expand + flatten (count)");
   CK(c, c->d_counters.ensure(64));
   CK(c, cudaMemsetAsync(c->d_counters.p, 0, 64, st));
   CK(c, cudaEventRecord(c->ev[0], st));
@@ -552,6 +561,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   }
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
 
+  nvtxRangePop();
+  nvtxRangePushA("z2d K2 setup + K3b list sizes + read-back");
   // K2: per-draw regions and (draw, tile-row) slots; K3b (count half): sizes of the per-tile-row draw lists.  Both only need
   // the extents gathered by the count pass, so they run before the edges exist and the three totals the host needs for
   // allocation come back in ONE round trip.
@@ -574,6 +585,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   const unsigned long long sim_rows = *reinterpret_cast<unsigned long long*>(c->h_total + 4),
                            sim_slots = *reinterpret_cast<unsigned long long*>(c->h_total + 6);
 
+  nvtxRangePop();
+  nvtxRangePushA("z2d K1 flatten (emit) + edge replay");
   // K1 (emit half)
   CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
   CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
@@ -599,6 +612,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   }
   CK(c, cudaEventRecord(c->ev[1], st));
 
+  nvtxRangePop();
+  nvtxRangePushA("z2d K3 bin edges + tile-row lists");
   // K3a: edges -> (draw, tile-row) lists
   launch_assign_band_base(c->d_draws.as<DevDraw>(), n_draws, c->d_draw_band_off.as<uint32_t>(), c->d_hots.as<DrawHot>(), c->d_boxes.as<DrawBox>(),
                           S.sfcs, st);
@@ -624,6 +639,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
                     c->d_band_xr.as<uint2>(), st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
+  nvtxRangePop();
+  nvtxRangePushA("z2d K4 raster tiles");
   // K4: fused coverage + compositing
   RasterArgs A;
   A.sfcs = S.sfcs;
@@ -643,6 +660,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   launch_raster(A, m.n_strokes != 0 || m.n_srcs != 0, st);
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev[4], st));
+  nvtxRangePop();
   launches += 9;
 
   z2d_stats& s = c->stats;
@@ -1428,6 +1446,35 @@ int32_t z2d_surface_paint_pixel(z2d_sfc* s, const z2d_pixel* px) {
   return Z2D_OK;
 }
 
+int32_t z2d_surface_downsample(z2d_sfc* s) {
+  if (!s || s->external || s->y0 != 0 || s->vh != s->h) return Z2D_E_INVALID_ARG;  // whole surfaces that own their pixels
+  if (s->w < 4 || s->h < 4) return Z2D_OK;  // surface.zig:448: nothing happens
+  z2d_ctx* c = s->ctx;
+  cudaSetDevice(c->device);
+  int rc = flush(c);
+  if (rc) return rc;
+  const int32_t w = s->w / 4, h = s->h / 4;
+  const size_t bytes = ((size_t)w * (size_t)h * (size_t)fmt_bits(s->fmt) + 7) / 8, alloc = (bytes + 31) & ~(size_t)15;
+  uint8_t* nd = nullptr;
+  cudaError_t e = cudaMalloc((void**)&nd, alloc);
+  if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? Z2D_E_OUT_OF_MEMORY : fail(c, "downsample", e);
+  CK(c, cudaMemsetAsync(nd, 0, alloc, c->stream));
+  launch_downsample(s->data, nd, s->fmt, s->w, w, h, c->stream);
+  CK(c, cudaGetLastError());
+  CK(c, cudaStreamSynchronize(c->stream));  // the old buffer is released: the reference resizes in place (surface.zig:471-490)
+  if (c->d2h_pending) {
+    CK(c, cudaStreamSynchronize(c->d2h_stream));
+    c->d2h_pending = false;
+  }
+  cudaFree(s->data);
+  s->data = nd;
+  s->w = w;
+  s->h = h;
+  s->vh = h;
+  s->bytes = bytes;
+  return Z2D_OK;
+}
+
 int32_t z2d_surface_put_pixel(z2d_sfc* s, int32_t x, int32_t y, const z2d_pixel* px) {
   if (!s || !px || px->format > Z2D_FMT_ALPHA1) return Z2D_E_INVALID_ARG;
   if (x < 0 || y < 0 || x >= s->w || y >= s->vh) return Z2D_OK;  // surface.zig:520,770
@@ -1918,6 +1965,7 @@ int32_t z2d_composite(z2d_ctx* c, z2d_sfc* dst, int32_t dst_x, int32_t dst_y, co
     if ((rc = conv(ops[k].dst, A.ops[k].dst, A.ops[k].has_dst, true))) return rc;
     if ((rc = conv(ops[k].src, A.ops[k].src, A.ops[k].has_src, false))) return rc;
   }
+  NvtxRange r_comp("z2d K5 composite");
   CK(c, upload(c, c->d_comp_grads, grads.data(), grads.size() * sizeof(DevGrad)));
   CK(c, upload(c, c->d_comp_stop_off, offs.data(), offs.size() * 4));
   CK(c, upload(c, c->d_comp_stop_col, cols.data(), cols.size() * sizeof(float4)));

@@ -56,6 +56,7 @@ def load_library():
         "z2d_surface_export_size": (C.c_size_t, [vp, C.c_uint32]),
         "z2d_surface_export": (C.c_int32, [vp, C.c_uint32, vp, C.c_size_t]),
         "z2d_surface_paint_pixel": (C.c_int32, [vp, P(abi.PixelPOD)]),
+        "z2d_surface_downsample": (C.c_int32, [vp]),
         "z2d_surface_put_pixel": (C.c_int32, [vp, C.c_int32, C.c_int32, P(abi.PixelPOD)]),
         "z2d_surface_get_pixel": (C.c_int32, [vp, C.c_int32, C.c_int32, P(abi.PixelPOD)]),
         "z2d_fill": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.Node), C.c_size_t, P(abi.FillOptsPOD)]),
@@ -75,7 +76,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_destroy", "z2d_ctx_set_chunk", "z2d_flush", "z2d_sync",
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_band_view", "z2d_surface_ipc_export", "z2d_surface_open_peer_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
-                    "z2d_surface_download", "z2d_surface_download_async", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel",
+                    "z2d_surface_download", "z2d_surface_download_async", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel", "z2d_surface_downsample",
                     "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
 
 
@@ -157,6 +158,10 @@ class CudaBackend:
 
     def surface_put_pixel(self, hd, x, y, px):
         self._check(self.lib.z2d_surface_put_pixel(hd, x, y, C.byref(px.pod())))
+
+    def surface_downsample(self, hd):
+        self._check(self.lib.z2d_surface_downsample(hd))
+        return self.lib.z2d_surface_width(hd), self.lib.z2d_surface_height(hd)
 
     def surface_get_pixel(self, hd, x, y):
         """(format, r, g, b, a) as stored, or None where Surface.getPixel returns null."""

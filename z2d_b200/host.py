@@ -652,6 +652,10 @@ class Surface:
     def paint_pixel(self, px):  # surface.zig:295
         self.backend.surface_paint_pixel(self.handle, px)
 
+    def downsample(self):  # surface.zig:447-490: 4x box average in place, dimensions / 4
+        self.width, self.height = self.backend.surface_downsample(self.handle)
+        self.canvas_height = self.height
+
     def put_pixel(self, x, y, px):  # surface.zig:288
         self.backend.surface_put_pixel(self.handle, int(x), int(y), px)
 
