@@ -377,35 +377,11 @@ __global__ void k_mark_nodes(const DevSubPath* __restrict__ sps, uint32_t n_sp, 
   for (uint32_t k = sp.node_begin; k < sp.node_end; k++) node_sp[k] = i;
 }
 
-// Thread per node for line_to / close_path (one edge at most); curve_to nodes are collected into a dense list (count pass)
-// and flattened by k_flatten_curves so that every lane of its warps runs the subdivision loop.
-template <bool EMIT, bool CURVES>
-__global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
-                                const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
-                                const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw,
-                                uint32_t* __restrict__ curve_list, uint32_t* __restrict__ n_curves) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (CURVES) {  // i indexes the curve list
-    if (i >= *n_curves) return;
-    i = curve_list[i];
-  } else if (i >= n_nodes) {
-    return;
-  }
-  const uint32_t spi = node_sp[i];
-  if (spi == 0xffffffffu) {
-    if (!EMIT) counts[i] = 0;
-    return;
-  }
-  const DevSubPath sp = sps[spi];
-  const z2d_node nd = nodes[i];
-  if (nd.tag == Z2D_NODE_MOVE_TO) {
-    if (!EMIT) counts[i] = 0;
-    return;
-  }
-  if (!CURVES && nd.tag == Z2D_NODE_CURVE_TO) {
-    if (!EMIT) curve_list[atomicAdd(n_curves, 1u)] = i;  // (nvcc aggregates the increment per warp)
-    return;
-  }
+// One node of a node-parallel sub-path (line_to / curve_to / close_path): count (EMIT = false: also extents) or emit its edges.
+template <bool EMIT>
+Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws,
+                        uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges,
+                        uint32_t* __restrict__ edge_draw) {
   DevDraw& d = draws[sp.draw];
   EdgeSink<EMIT> sink;
   sink.scale = d.scale;
@@ -462,16 +438,46 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
   }
 }
 
+// Thread per node for line_to / close_path (one edge at most); curve_to nodes are collected into a dense list (count pass)
+// and flattened by k_flatten_curves so that every lane of its warps runs the subdivision loop.
+template <bool EMIT, bool CURVES>
+__global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
+                                const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
+                                const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw,
+                                uint32_t* __restrict__ curve_list, uint32_t* __restrict__ n_curves) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (CURVES) {  // i indexes the curve list
+    if (i >= *n_curves) return;
+    i = curve_list[i];
+  } else if (i >= n_nodes) {
+    return;
+  }
+  const uint32_t spi = node_sp[i];
+  if (spi == 0xffffffffu) {
+    if (!EMIT) counts[i] = 0;
+    return;
+  }
+  const DevSubPath sp = sps[spi];
+  const z2d_node nd = nodes[i];
+  if (nd.tag == Z2D_NODE_MOVE_TO) {
+    if (!EMIT) counts[i] = 0;
+    return;
+  }
+  if (!CURVES && nd.tag == Z2D_NODE_CURVE_TO) {
+    if (!EMIT) curve_list[atomicAdd(n_curves, 1u)] = i;  // (nvcc aggregates the increment per warp)
+    return;
+  }
+  flatten_node<EMIT>(i, sp, nd, nodes, draws, counts, offs, edges, edge_draw);
+}
+
 // =====================================================================================
 // K2: per-draw setup (regions, tile ranges)
 // =====================================================================================
 Z2D_D int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
 
 // DrawIn (+ side tables) -> DevDraw; also (re)initialises everything the pipeline writes, so a replay starts clean
-__global__ void k_expand_draws(const DrawIn* __restrict__ in, const StrokeIn* __restrict__ strokes, const DevSrc* __restrict__ srcs,
-                               DevDraw* __restrict__ draws, uint32_t n_draws) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_draws) return;
+Z2D_D void expand_draw(uint32_t i, const DrawIn* __restrict__ in, const StrokeIn* __restrict__ strokes, const DevSrc* __restrict__ srcs,
+                        DevDraw* __restrict__ draws) {
   const DrawIn q = in[i];
   DevDraw d;
   memset(&d, 0, sizeof d);
@@ -507,11 +513,15 @@ __global__ void k_expand_draws(const DrawIn* __restrict__ in, const StrokeIn* __
   d.ext[3] = f64_order(-INFINITY);
   draws[i] = d;
 }
-
-__global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
-                              uint32_t* __restrict__ draw_bands, DrawBox* __restrict__ boxes, unsigned long long* __restrict__ counters) {
+__global__ void k_expand_draws(const DrawIn* __restrict__ in, const StrokeIn* __restrict__ strokes, const DevSrc* __restrict__ srcs,
+                               DevDraw* __restrict__ draws, uint32_t n_draws) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
+  expand_draw(i, in, strokes, srcs, draws);
+}
+
+Z2D_D void setup_draw(uint32_t i, DevDraw* __restrict__ draws, const DevSurface* __restrict__ sfcs, uint32_t* __restrict__ draw_bands,
+                       DrawBox* __restrict__ boxes, unsigned long long* __restrict__ counters) {
   DevDraw& d = draws[i];
   const DevSurface s = sfcs[d.surface];
   d.valid = 0;
@@ -596,12 +606,16 @@ __global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, con
   draw_bands[i] = (uint32_t)(d.ey1 - d.ey0 + 1);
   if (counters && ry1 > ry0) atomicAdd(&counters[1], (unsigned long long)(rx1 - rx0) * (unsigned long long)(ry1 - ry0));
 }
-
-// second half of the setup: (draw, tile-row) slot base + the compact record the raster kernel reads
-__global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off,
-                                   DrawHot* __restrict__ hots, DrawBox* __restrict__ boxes, const DevSurface* __restrict__ sfcs) {
+__global__ void k_setup_draws(DevDraw* __restrict__ draws, uint32_t n_draws, const DevSurface* __restrict__ sfcs,
+                              uint32_t* __restrict__ draw_bands, DrawBox* __restrict__ boxes, unsigned long long* __restrict__ counters) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_draws) return;
+  setup_draw(i, draws, sfcs, draw_bands, boxes, counters);
+}
+
+// second half of the setup: (draw, tile-row) slot base + the compact record the raster kernel reads
+Z2D_D void assign_band_base(uint32_t i, DevDraw* __restrict__ draws, const uint32_t* __restrict__ band_off, DrawHot* __restrict__ hots,
+                             DrawBox* __restrict__ boxes, const DevSurface* __restrict__ sfcs) {
   DevDraw& d = draws[i];
   d.band_base = band_off[i];
   {
@@ -626,6 +640,12 @@ __global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws
   h.sim_base = d.sim_base; h.sim_y0 = d.sim_y0; h.sim_rows = d.sim_rows;
   hots[i] = h;
 }
+__global__ void k_assign_band_base(DevDraw* __restrict__ draws, uint32_t n_draws, const uint32_t* __restrict__ band_off,
+                                   DrawHot* __restrict__ hots, DrawBox* __restrict__ boxes, const DevSurface* __restrict__ sfcs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_draws) return;
+  assign_band_base(i, draws, band_off, hots, boxes, sfcs);
+}
 
 // =====================================================================================
 // K3a: bin edges into (draw, tile-row) lists.  An edge is active on sub-scanline ys iff
@@ -646,23 +666,24 @@ Z2D_D bool edge_band_range(const DevEdge& e, const DevDraw& d, int& t0, int& t1)
   return true;
 }
 
-__global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
-                            const DevDraw* __restrict__ draws, uint32_t* __restrict__ band_count) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_edges) return;
+Z2D_D void bin_count_edge(uint32_t i, const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, const DevDraw* __restrict__ draws,
+                           uint32_t* __restrict__ band_count) {
   const DevDraw& d = draws[edge_draw[i]];
   if (!d.valid || d.mode == 2) return;
   int t0, t1;
   if (!edge_band_range(edges[i], d, t0, t1)) return;
   for (int t = t0; t <= t1; t++) atomicAdd(&band_count[d.band_base + (uint32_t)(t - d.ey0)], 1u);
 }
-
-__global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
-                              const DevDraw* __restrict__ draws, const uint32_t* __restrict__ band_off,
-                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges, int4* __restrict__ band_hdr,
-                              uint2* __restrict__ band_xr) {
+__global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
+                            const DevDraw* __restrict__ draws, uint32_t* __restrict__ band_count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
+  bin_count_edge(i, edges, edge_draw, draws, band_count);
+}
+
+Z2D_D void bin_scatter_edge(uint32_t i, const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, const DevDraw* __restrict__ draws,
+                             const uint32_t* __restrict__ band_off, uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges,
+                             int4* __restrict__ band_hdr, uint2* __restrict__ band_xr, uint32_t band_cap) {
   const DevDraw& d = draws[edge_draw[i]];
   if (!d.valid || d.mode == 2) return;
   const DevEdge e = edges[i];
@@ -691,11 +712,20 @@ __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t*
   for (int t = t0; t <= t1; t++) {
     const uint32_t b = d.band_base + (uint32_t)(t - d.ey0);
     const uint32_t slot = band_off[b] + atomicAdd(&band_cursor[b], 1u);
+    if (slot >= band_cap) continue;  // (small-batch path: fixed capacity, the batch is redone by the sized pipeline)
     band_edges[slot] = e;
     band_hdr[slot] = h;
     atomicMax(&band_xr[b].x, c_lo);
     atomicMax(&band_xr[b].y, c_hi);
   }
+}
+__global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
+                              const DevDraw* __restrict__ draws, const uint32_t* __restrict__ band_off,
+                              uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges, int4* __restrict__ band_hdr,
+                              uint2* __restrict__ band_xr) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_edges) return;
+  bin_scatter_edge(i, edges, edge_draw, draws, band_off, band_cursor, band_edges, band_hdr, band_xr, 0xffffffffu);
 }
 
 
@@ -803,24 +833,11 @@ Z2D_D uint32_t find_surface_by(const DevSurface* sfcs, uint32_t n_sfc, const uin
   return lo;
 }
 
+// The draws [b, e) of one surface against one of its tile rows: count them (WRITE = false) or write their list items at o.
 template <bool WRITE>
-__global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
-                             const uint32_t* __restrict__ chunk_base, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
-                             const uint32_t* __restrict__ off, uint4* __restrict__ items, const uint32_t* __restrict__ band_off,
-                             const uint2* __restrict__ band_xr) {
-  // one block per (surface, chunk of kDrawChunk draws); threads stride over the surface's tile-rows, so every thread of a
-  // warp reads the SAME box at the same time (one broadcast transaction instead of 32 strided ones)
-  const uint32_t si = find_surface_by(sfcs, n_sfc, chunk_base, blockIdx.x);
-  const DevSurface s = sfcs[si];
-  const uint32_t n_draws = s.draw_end - s.draw_begin;
-  const uint32_t chunks = (n_draws + kDrawChunk - 1) / kDrawChunk;
-  const uint32_t chunk = blockIdx.x - chunk_base[si];
-  const uint32_t b = s.draw_begin + chunk * kDrawChunk;
-  const uint32_t e = min(b + kDrawChunk, s.draw_end);
-  for (int band = (int)threadIdx.x; band < s.tiles_y; band += (int)blockDim.x) {
-    const uint32_t w = work_base[si] + (uint32_t)band * chunks + chunk;
+Z2D_D uint32_t band_list_row(int band, uint32_t b, uint32_t e, const DrawBox* __restrict__ boxes, uint32_t o, uint4* __restrict__ items,
+                             const uint32_t* __restrict__ band_off, const uint2* __restrict__ band_xr) {
     uint32_t n = 0;
-    const uint32_t o = WRITE ? off[w] : 0u;
     for (uint32_t i = b; i < e; i++) {
       const int4 d = __ldg(reinterpret_cast<const int4*>(boxes) + 2 * i);  // {tx0, tx1, ty0, ty1}
       if (d.x >= 0 && band >= d.z && band <= d.w) {
@@ -851,6 +868,27 @@ __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc
         n++;
       }
     }
+    return n;
+}
+
+template <bool WRITE>
+__global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
+                             const uint32_t* __restrict__ chunk_base, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
+                             const uint32_t* __restrict__ off, uint4* __restrict__ items, const uint32_t* __restrict__ band_off,
+                             const uint2* __restrict__ band_xr) {
+  // one block per (surface, chunk of kDrawChunk draws); threads stride over the surface's tile-rows, so every thread of a
+  // warp reads the SAME box at the same time (one broadcast transaction instead of 32 strided ones)
+  const uint32_t si = find_surface_by(sfcs, n_sfc, chunk_base, blockIdx.x);
+  const DevSurface s = sfcs[si];
+  const uint32_t n_draws = s.draw_end - s.draw_begin;
+  const uint32_t chunks = (n_draws + kDrawChunk - 1) / kDrawChunk;
+  const uint32_t chunk = blockIdx.x - chunk_base[si];
+  const uint32_t b = s.draw_begin + chunk * kDrawChunk;
+  const uint32_t e = min(b + kDrawChunk, s.draw_end);
+  for (int band = (int)threadIdx.x; band < s.tiles_y; band += (int)blockDim.x) {
+    const uint32_t w = work_base[si] + (uint32_t)band * chunks + chunk;
+    const uint32_t o = WRITE ? off[w] : 0u;
+    const uint32_t n = band_list_row<WRITE>(band, b, e, boxes, o, items, band_off, band_xr);
     if (!WRITE) cnt[w] = n;
   }
 }
@@ -1040,6 +1078,7 @@ __global__ void k_put_pixel(uint8_t* data, uint32_t fmt, size_t idx, uint32_t ra
 
 }  // namespace z2d
 #include "composite.cuh"
+#include "smallbatch.cuh"
 namespace z2d {
 
 // ------------------------------------------------------------------------- launchers
@@ -1109,6 +1148,7 @@ void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* s
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {
   if (n_draws) k_edge_sim<<<blocks_for(n_draws, 64), 64, 0, st>>>(draws, n_draws, sfcs, edges, sp_off, perm, xs, rows);
 }
+void launch_small_batch(const SmallArgs& A, cudaStream_t st) { k_small_batch<<<1, kSmallThreads, 0, st>>>(A); }
 void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st) {
   if (!A.n_tiles) return;
   if (rich) k_raster_tiles_rich<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);

@@ -25,6 +25,7 @@ struct RasterArgs {
   const int4* band_hdr;        // per binned edge: {xlo, xhi, first row | dir<<31, last row}
   unsigned long long* counters;  // [0] covered pixels, [1] region pixels (may be null)
   const int4* sim_rows;        // row records of k_edge_sim (draws flagged kDrawUnpaired / kDrawRowRecords)
+  const uint32_t* abort;       // small-batch path: non-zero => the prepare kernel gave up, composite nothing (may be null)
   GradTables T;
 };
 
@@ -76,6 +77,40 @@ void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const
 // exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);
+// ---- small batches in two launches (smallbatch.cuh)
+constexpr uint32_t kSmallMaxDraws = 64, kSmallMaxNodes = 4096, kSmallMaxSubPaths = 1024, kSmallMaxWork = 4096;
+constexpr uint32_t kSmallEdgeCap = 1u << 18, kSmallBandCap = 1u << 19, kSmallSlotCap = 1u << 14, kSmallItemCap = 1u << 14;
+constexpr int kSmallThreads = 512;
+
+struct SmallArgs {
+  const DrawIn* draws_in;
+  const StrokeIn* strokes;
+  const DevSrc* srcs;
+  const DevSubPath* sps;
+  const z2d_node* nodes;
+  const DevSurface* sfcs;
+  const uint32_t* work_base;
+  uint32_t n_draws, n_sp, n_nodes, n_sfc, n_work;
+  DevDraw* draws;
+  DrawHot* hots;
+  DrawBox* boxes;
+  uint32_t* draw_bands;     // n_draws + 1 (scanned in place)
+  uint32_t* node_sp;        // n_nodes
+  uint32_t* cnt;            // n_sp + n_nodes + 1 (scanned in place -> offsets)
+  DevEdge* edges;
+  uint32_t* edge_draw;
+  uint32_t* band_count;     // kSmallSlotCap + 1 (scanned in place -> band_off)
+  uint32_t* band_cursor;
+  uint2* band_xr;
+  DevEdge* band_edges;
+  int4* band_hdr;
+  uint32_t* list_cnt;       // n_work + 1 (scanned in place -> list_off)
+  uint4* list_items;
+  unsigned long long* counters;
+  uint32_t* out;            // device copy of the result block: [0] abort reason, [1] edges, [2] slots, [3] items, [4] binned edges
+};
+
+void launch_small_batch(const SmallArgs& A, cudaStream_t st);
 // rich: the batch holds strokes or gradient / dither sources (k_raster_tiles_rich, see raster.cuh)
 void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st);
 // isolated single-draw modes (slowpath.cuh)

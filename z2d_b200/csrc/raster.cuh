@@ -179,9 +179,12 @@ Z2D_D int edge_col(const double4& ev, double top, int ys, int sx0, int ncols) {
 // header helpers: {xlo, xhi, first active row | dir << 31, last active row} (k_bin_scatter)
 Z2D_D bool hdr_active(const int4& h, int ys) { return ys >= (h.z & 0x7fffffff) && ys <= h.w; }  // == top < ys + 0.5 <= bottom
 
+constexpr uint32_t kCrossListCap = 128;  // crossing-edge positions kept per (draw, tile) by tile_cover
+
 template <int W, bool TWO>
-Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, uint64_t cross_bits, int ys0, int sx0,
-                      int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1, uint32_t& n_eval) {
+Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, const uint16_t* __restrict__ clist,
+                      uint32_t ncross, int ys0, int sx0, int ncols, bool even_odd, int wl0, int wl1, uint64_t& m0, uint64_t& m1,
+                      uint32_t& n_eval) {
   uint64_t p0[W], p1[TWO ? W : 1];
 #pragma unroll
   for (int k = 0; k < W; k++) {  // start from the backdrop winding (two's complement, bit-sliced)
@@ -207,13 +210,14 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
       }
     }
   };
-  if (n_be <= 64) {
+  // `clist`: positions (in the band) of the edges that cross the tile, compacted by tile_cover's classification pass -- a text
+  // run bins hundreds of edges per tile row of which a tile sees a few dozen
+  if (ncross <= 64) {
     // Which of the crossing edges are live on THIS lane's rows (warp-uniform loop, integer tests only) ...
     uint64_t my0 = 0, my1 = 0, up_bits = 0;
-    for (uint64_t b = cross_bits; b; b &= b - 1) {
-      const int i = __ffsll((long long)b) - 1;
-      const int4 h = __ldg(hd + i);
-      const uint64_t bit = 1ull << i;
+    for (uint32_t k = 0; k < ncross; k++) {
+      const int4 h = __ldg(hd + clist[k]);
+      const uint64_t bit = 1ull << k;
       if (hdr_active(h, ys0)) my0 |= bit;
       if (TWO && hdr_active(h, ys0 + 1)) my1 |= bit;
       if (h.z < 0) up_bits |= bit;
@@ -221,11 +225,18 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
     // ... then every lane walks only its own edges: the warp iterates max-over-rows(edges per row) times, not once per
     // crossing edge of the tile, and no lane idles on an edge that does not reach its rows.
     for (uint64_t mine = my0 | my1; mine; mine &= mine - 1) {
-      const int i = __ffsll((long long)mine) - 1;
-      const uint64_t bit = 1ull << i;
-      apply(ld_edge(be + i), (up_bits & bit) != 0, (my0 & bit) != 0, (my1 & bit) != 0);
+      const int k = __ffsll((long long)mine) - 1;
+      const uint64_t bit = 1ull << k;
+      apply(ld_edge(be + clist[k]), (up_bits & bit) != 0, (my0 & bit) != 0, (my1 & bit) != 0);
     }
-  } else {
+  } else if (ncross <= kCrossListCap) {
+    for (uint32_t k = 0; k < ncross; k++) {
+      const uint32_t i = clist[k];
+      const int4 h = __ldg(hd + i);
+      const bool a0 = hdr_active(h, ys0), a1 = TWO && hdr_active(h, ys0 + 1);
+      if (a0 || a1) apply(ld_edge(be + i), h.z < 0, a0, a1);
+    }
+  } else {  // (the list overflowed: every edge of the band)
     for (uint32_t i = 0; i < n_be; i++) {
       const int4 h = __ldg(hd + i);
       const bool a0 = hdr_active(h, ys0), a1 = TWO && hdr_active(h, ys0 + 1);
@@ -248,12 +259,16 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
 }
 
 // rare: more than 60 edges of one draw cross one tile; 32 planes in local memory, one row at a time
-__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be, int ys, int sx0,
-                                                int ncols, bool even_odd, int wl) {
+__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be,
+                                                const uint16_t* __restrict__ clist, uint32_t ncross, int ys, int sx0, int ncols, bool even_odd,
+                                                int wl) {
   uint64_t p[32];
   for (int k = 0; k < 32; k++) p[k] = ((wl >> k) & 1) ? ~0ull : 0ull;
   const int sx_hi = sx0 + ncols;
-  for (uint32_t i = 0; i < n_be; i++) {
+  const bool listed = ncross <= kCrossListCap;
+  const uint32_t n_it = listed ? ncross : n_be;
+  for (uint32_t it = 0; it < n_it; it++) {
+    const uint32_t i = listed ? (uint32_t)clist[it] : it;
     const int4 h = __ldg(hd + i);
     if (h.x > sx_hi || h.y < sx0 || !hdr_active(h, ys)) continue;
     const double4 ev = ld_edge(be + i);
@@ -289,9 +304,9 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
   wdiff[lane] = 0;
   wdiff[lane + 32] = 0;
   if (lane == 0) wdiff[64] = 0;
+  uint16_t* clist = reinterpret_cast<uint16_t*>(wdiff + 68);  // kCrossListCap entries behind the 65 difference slots (528-byte scratch)
   __syncwarp();
   uint32_t ncross = 0;
-  uint64_t cross_bits = 0;
   for (uint32_t base = 0; base < n_be; base += 32) {
     const uint32_t i = base + (uint32_t)lane;
     bool cross = false;
@@ -311,9 +326,13 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
       }
     }
     const uint32_t b = __ballot_sync(0xffffffffu, cross);
+    if (cross) {
+      const uint32_t k = ncross + (uint32_t)__popc(b & ((1u << lane) - 1u));
+      if (k < kCrossListCap && i < 65536u) clist[k] = (uint16_t)i;
+    }
     ncross += (uint32_t)__popc(b);
-    if (base < 64) cross_bits |= (uint64_t)b << base;
   }
+  if (n_be > 65536u && ncross <= kCrossListCap) ncross = kCrossListCap + 1;  // (positions would not fit 16 bits: full loops)
   __syncwarp();
   int wl0, wl1 = 0;
   {  // prefix sum of the difference array -> backdrop winding of this lane's rows
@@ -343,15 +362,15 @@ Z2D_D void tile_cover(const DevEdge* __restrict__ be, const int4* __restrict__ h
   const bool full1 = !even_odd && (wl1 > (int)ncross || -wl1 > (int)ncross);
   const int b0 = full0 ? 0 : wl0, b1 = full1 ? 0 : wl1;
   if (ncross <= 7) {
-    if (two) cross_pass<5, true>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
-    else cross_pass<5, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
+    if (two) cross_pass<5, true>(be, hd, n_be, clist, ncross, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
+    else cross_pass<5, false>(be, hd, n_be, clist, ncross, ys0, sx0, ncols, even_odd, b0, b1, m0, m1, n_eval);
   } else if (ncross <= 60) {
     uint64_t dummy = 0;
-    cross_pass<8, false>(be, hd, n_be, cross_bits, ys0, sx0, ncols, even_odd, b0, 0, m0, dummy, n_eval);
-    if (two) cross_pass<8, false>(be, hd, n_be, cross_bits, ys0 + 1, sx0, ncols, even_odd, b1, 0, m1, dummy, n_eval);
+    cross_pass<8, false>(be, hd, n_be, clist, ncross, ys0, sx0, ncols, even_odd, b0, 0, m0, dummy, n_eval);
+    if (two) cross_pass<8, false>(be, hd, n_be, clist, ncross, ys0 + 1, sx0, ncols, even_odd, b1, 0, m1, dummy, n_eval);
   } else {
-    m0 = cross_row_wide(be, hd, n_be, ys0, sx0, ncols, even_odd, b0);
-    m1 = two ? cross_row_wide(be, hd, n_be, ys0 + 1, sx0, ncols, even_odd, b1) : 0ull;
+    m0 = cross_row_wide(be, hd, n_be, clist, ncross, ys0, sx0, ncols, even_odd, b0);
+    m1 = two ? cross_row_wide(be, hd, n_be, clist, ncross, ys0 + 1, sx0, ncols, even_odd, b1) : 0ull;
   }
   if (full0) m0 = ~0ull;
   if (full1) m1 = ~0ull;
@@ -722,6 +741,7 @@ Z2D_D void raster_tiles_body(const RasterArgs& A) {
   const int warp = kRasterThreads == 32 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t gt = blockIdx.x * (kRasterThreads / 32) + warp;
   if (gt >= A.n_tiles) return;
+  if (A.abort && *A.abort) return;  // (small-batch path: the prepare kernel gave up; the sized pipeline redoes the batch)
   // tile -> surface, tx, ty
   uint32_t si;
   {

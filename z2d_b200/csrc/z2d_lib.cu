@@ -193,6 +193,10 @@ struct z2d_ctx {
   DevBuf d_counters, d_boxes, d_hots, d_band_hdr, d_band_xr;
   DevBuf d_export, d_gamma;  // z2d_surface_export: scanline staging, sRGB channel table
   DevBuf d_sim_rows, d_sim_perm, d_sim_x;  // k_edge_sim: row records, per-edge scratch
+  DevBuf d_small_out;                      // small-batch path: the prepare kernel's result block (abort flag, totals)
+  uint32_t* h_small = nullptr;             // its pinned host copy
+  bool small_pending = false;              // a small batch is on the stream and its abort flag has not been looked at yet
+  bool small_enabled = true;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   BatchMeta last;
   bool stats_pending = false;
@@ -656,6 +660,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   A.band_hdr = c->d_band_hdr.as<int4>();
   A.counters = c->d_counters.as<unsigned long long>();
   A.sim_rows = c->d_sim_rows.as<int4>();
+  A.abort = nullptr;
   A.T = tables(c, S.grads, S.stop_off, S.stop_col);
   launch_raster(A, m.n_strokes != 0 || m.n_srcs != 0, st);
   CK(c, cudaGetLastError());
@@ -674,6 +679,110 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   s.kernel_launches = launches;
   s.h2d_bytes = replay ? 0 : m.h2d_bytes;
   c->stats_pending = true;
+  return Z2D_OK;
+}
+
+// Small batches: everything before the raster kernel in ONE single-CTA launch into fixed-capacity buffers (smallbatch.cuh),
+// no host read-back.  The prepare kernel may give up (capacity, or a draw that needs the scanline replay): check_small, run
+// before the context is used again, then redoes the batch with the sized pipeline -- its inputs are still resident and the
+// raster kernel of the abandoned attempt composited nothing.
+int run_small(z2d_ctx* c) {
+  const BatchMeta& m = c->last;
+  InputSet& S = c->in[m.set];
+  cudaStream_t st = c->stream;
+  const uint32_t n_nodes = (uint32_t)m.n_nodes;
+  CK(c, c->d_counters.ensure(64));
+  CK(c, c->d_small_out.ensure(32));
+  CK(c, c->d_hots.ensure((size_t)kSmallMaxDraws * sizeof(DrawHot)));
+  CK(c, c->d_boxes.ensure((size_t)kSmallMaxDraws * sizeof(DrawBox)));
+  CK(c, c->d_draw_bands.ensure(((size_t)kSmallMaxDraws + 1) * 4));
+  CK(c, c->d_node_sp.ensure((size_t)kSmallMaxNodes * 4));
+  CK(c, c->d_sp_count.ensure(((size_t)kSmallMaxSubPaths + kSmallMaxNodes + 1) * 4));
+  CK(c, c->d_edges.ensure((size_t)kSmallEdgeCap * sizeof(DevEdge)));
+  CK(c, c->d_edge_draw.ensure((size_t)kSmallEdgeCap * 4));
+  CK(c, c->d_band_count.ensure(((size_t)kSmallSlotCap + 1) * 4));
+  CK(c, c->d_band_cursor.ensure(((size_t)kSmallSlotCap + 1) * 4));
+  CK(c, c->d_band_xr.ensure(((size_t)kSmallSlotCap + 1) * sizeof(uint2)));
+  CK(c, c->d_band_edges.ensure((size_t)kSmallBandCap * sizeof(DevEdge)));
+  CK(c, c->d_band_hdr.ensure((size_t)kSmallBandCap * sizeof(int4)));
+  CK(c, c->d_list_cnt.ensure(((size_t)kSmallMaxWork + 1) * 4));
+  CK(c, c->d_list_items.ensure((size_t)kSmallItemCap * sizeof(uint4)));
+  SmallArgs P;
+  P.draws_in = S.d_draws_in.as<DrawIn>();
+  P.strokes = S.strokes;
+  P.srcs = S.srcs;
+  P.sps = S.d_subpaths.as<DevSubPath>();
+  P.nodes = S.d_nodes.as<z2d_node>();
+  P.sfcs = S.sfcs;
+  P.work_base = S.work_base;
+  P.n_draws = m.n_draws; P.n_sp = m.n_sp; P.n_nodes = n_nodes; P.n_sfc = m.n_sfc; P.n_work = m.n_work;
+  P.draws = c->d_draws.as<DevDraw>();
+  P.hots = c->d_hots.as<DrawHot>();
+  P.boxes = c->d_boxes.as<DrawBox>();
+  P.draw_bands = c->d_draw_bands.as<uint32_t>();
+  P.node_sp = c->d_node_sp.as<uint32_t>();
+  P.cnt = c->d_sp_count.as<uint32_t>();
+  P.edges = c->d_edges.as<DevEdge>();
+  P.edge_draw = c->d_edge_draw.as<uint32_t>();
+  P.band_count = c->d_band_count.as<uint32_t>();
+  P.band_cursor = c->d_band_cursor.as<uint32_t>();
+  P.band_xr = c->d_band_xr.as<uint2>();
+  P.band_edges = c->d_band_edges.as<DevEdge>();
+  P.band_hdr = c->d_band_hdr.as<int4>();
+  P.list_cnt = c->d_list_cnt.as<uint32_t>();
+  P.list_items = c->d_list_items.as<uint4>();
+  P.counters = c->d_counters.as<unsigned long long>();
+  P.out = c->d_small_out.as<uint32_t>();
+  NvtxRange r("z2d small batch");
+  CK(c, cudaEventRecord(c->ev[0], st));
+  launch_small_batch(P, st);
+  for (int i = 1; i <= 3; i++) CK(c, cudaEventRecord(c->ev[i], st));
+  RasterArgs A;
+  A.sfcs = S.sfcs;
+  A.n_sfc = m.n_sfc;
+  A.n_tiles = m.n_tiles;
+  A.work_base = S.work_base;
+  A.list_off = P.list_cnt;
+  A.list_items = P.list_items;
+  A.draws = P.draws;
+  A.hots = P.hots;
+  A.band_off = P.band_count;
+  A.band_edges = P.band_edges;
+  A.band_hdr = P.band_hdr;
+  A.counters = P.counters;
+  A.sim_rows = nullptr;
+  A.abort = P.out;
+  A.T = tables(c, S.grads, S.stop_off, S.stop_col);
+  launch_raster(A, m.n_srcs != 0 || getenv("Z2D_SMALL_RICH") != nullptr, st);
+  CK(c, cudaGetLastError());
+  CK(c, cudaEventRecord(c->ev[4], st));
+  CK(c, cudaMemcpyAsync(c->h_small, P.out, 32, cudaMemcpyDeviceToHost, st));
+  c->small_pending = true;
+  z2d_stats& s = c->stats;
+  memset(&s, 0, sizeof s);
+  s.draws = m.n_draws;
+  s.nodes = m.n_nodes;
+  s.tiles = m.n_tiles;
+  s.kernel_launches = 2;
+  s.h2d_bytes = m.h2d_bytes;
+  c->stats_pending = true;
+  return Z2D_OK;
+}
+
+// Looks at the abort flag of the small batch on the stream, if any (blocks until that batch is done), and redoes an
+// abandoned batch with the sized pipeline.  Called before anything else touches the context.
+int check_small(z2d_ctx* c) {
+  if (!c->small_pending) return Z2D_OK;
+  c->small_pending = false;
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (c->h_small[0] != 0u) {
+    const int rc = run_pipeline(c, false);
+    if (c->last.valid) cudaEventRecord(c->in[c->last.set].done, c->stream);  // the next upload into this input set waits for the redo
+    return rc;
+  }
+  c->stats.edges = c->h_small[1];
+  c->stats.tile_items = c->h_small[3];
+  c->stats.band_edges = c->h_small[4];
   return Z2D_OK;
 }
 
@@ -706,6 +815,10 @@ int run_isolated(z2d_ctx* c, Batch& B) {
 }
 
 int flush_impl(z2d_ctx* c, Batch& B) {
+  {
+    const int rc0 = check_small(c);  // (before c->last is overwritten: an abandoned small batch is redone first)
+    if (rc0 != Z2D_OK) return rc0;
+  }
   const uint32_t n_draws = (uint32_t)B.draws.n;
   if (n_draws == 0) {
     clear_batch(c, B);
@@ -825,7 +938,10 @@ int flush_impl(z2d_ctx* c, Batch& B) {
                 B.pens.size() * 8 + B.dashes.size() * 8 +
                 sfcs.size() * sizeof(DevSurface) + work_base.size() * 4 + B.grads.size() * sizeof(DevGrad) +
                 B.stop_offsets.size() * 4 + B.stop_colors.size() * sizeof(float4);
-  int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) == 1u) ? run_isolated(c, B) : run_pipeline(c, false);
+  bool small = c->small_enabled && n_draws <= kSmallMaxDraws && B.nodes.n <= kSmallMaxNodes && n_sp <= kSmallMaxSubPaths && n_work <= kSmallMaxWork &&
+               B.strokes.empty();
+  for (uint32_t i = 0; small && i < n_draws; i++) small = ((B.draws.p[i].opts >> 11) & 3u) == 0u;  // no hairline / row-record draws
+  int rc = (n_draws == 1 && ((B.draws.p[0].opts >> 11) & 3u) == 1u) ? run_isolated(c, B) : (small ? run_small(c) : run_pipeline(c, false));
   cudaEventRecord(S.done, c->stream);  // (also on failure: the set is reusable after whatever was enqueued)
   S.used = true;
   clear_batch(c, B);
@@ -886,7 +1002,10 @@ int flush(z2d_ctx* c) {
   cudaSetDevice(c->device);
   int rc = wait_idle(c);
   int rc2 = execute_batch(c, *c->rec);
-  return rc != Z2D_OK ? rc : rc2;
+  // A small batch may have been abandoned by its prepare kernel; whatever the caller enqueues or reads next must come after
+  // its redo, so the flag is looked at here (one stream sync per small batch instead of the sized pipeline's two read-backs).
+  const int rc3 = check_small(c);
+  return rc != Z2D_OK ? rc : (rc2 != Z2D_OK ? rc2 : rc3);
 }
 
 uint32_t batch_slot(z2d_ctx* c, z2d_sfc* s) {
@@ -1085,7 +1204,8 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
   for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
-  if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
+  c->small_enabled = getenv("Z2D_NO_SMALL_BATCH") == nullptr;
+  if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&c->h_small, 32, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
       cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
     delete c;
     return Z2D_E_DEVICE;
@@ -1116,6 +1236,8 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   c->d_export.release();
   c->d_gamma.release();
+  c->d_small_out.release();
+  if (c->h_small) cudaFreeHost(c->h_small);
   c->d_sim_rows.release();
   c->d_sim_perm.release();
   c->d_sim_x.release();
@@ -1178,6 +1300,11 @@ int32_t z2d_get_stats(const z2d_ctx* cc, z2d_stats* out) {
   if (!cc || !out) return Z2D_E_INVALID_ARG;
   z2d_ctx* c = const_cast<z2d_ctx*>(cc);
   wait_idle(c);
+  {
+    cudaSetDevice(c->device);
+    const int rc0 = check_small(c);
+    if (rc0 != Z2D_OK) return rc0;
+  }
   if (c->stats_pending) {  // device counters and stage timings of the last batch
     cudaSetDevice(c->device);
     CK(c, cudaStreamSynchronize(c->stream));
