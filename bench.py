@@ -416,6 +416,20 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_c5:
         c5 = bench_extra.run_c5(cb, rank, world, ddist, args.scenes, 1024, 2, 1, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
+    # ---- the other single-GPU configurations, so that one default run (the driver's) carries every BASELINE config:
+    # config 1 (logo latency), config 3 (strokes, device step) and the config-4 compositor sweep (summary; cells: --workload c4)
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras["c1"] = bench_extra.run_c1(cb, reps=300, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001  (the logo scene needs the reference test fonts under tests/golden/fonts)
+            extras["c1"] = {"error": repr(e)}
+        extras["c3"] = bench_extra.run_c3(cb, args.strokes)
+        pk, _ = peaks()
+        cells = bench_extra.run_c4(cb, pk, full=False)
+        extras["c4_summary"] = bench_extra.c4_summary(cells)
+        extras["c4_context_fill"] = bench_extra.run_c4_fill(cb, pk)
+
     if rank == 0:
         peak, peak_kind = peaks()
         steps = args.steps
@@ -458,6 +472,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_composite": comp,
             "cpu_baseline": cpu,
             "c5": c5,
+            **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -511,6 +526,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-composite", action="store_true", help="skip the K5 roofline leg (profiling runs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 block of the default line (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 3 / 4 blocks of the default line (profiling runs)")
     ap.add_argument("--quick", action="store_true", help="c4: one operator per cell group")
     ap.add_argument("--band-size", type=int, default=16384, help="band: canvas edge in pixels")
     ap.add_argument("--verify", action="store_true", help="band: compare the stacked canvas with a single-GPU render")

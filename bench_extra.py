@@ -419,3 +419,36 @@ def run_c1(cb, reps=1000, with_cpu=True):
         out["cpu_baseline"] = {"value": cpu_us, "unit": "us/scene", "cores": 1, "kind": "port",
                                "sample": "50 scenes; C++ restatement of z2d's CPU path (oracle/), not z2d itself"}
     return out
+
+
+# ------------------------------------------------------------------------------------------------ config 3 (block of the default line)
+def run_c3(cb, n_strokes=50_000, steps=5):
+    """BASELINE config 3 as a block of the default line: device step of the 2048^2 stroke workload (resident batch, z2d_replay).
+    `python bench.py --workload c3` is the full line (e2e, CPU baseline, clocks)."""
+    import torch
+    scene = workloads.stroke_paths_scene(n_strokes, 2048, seed=0x7A326403)
+    sfc = Surface(Format.rgba, 2048, 2048, None, cb)
+    cmds = scene.draw_cmds(sfc.handle)
+    cb.set_chunk(0)
+    cb.submit(cmds.ctypes.data_as(C.POINTER(abi.DrawCmdPOD)), scene.n)
+    cb.sync()
+    zero = Pixel.rgba(0, 0, 0, 0)
+    for _ in range(2):
+        sfc.paint_pixel(zero)
+        cb.replay()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        sfc.paint_pixel(zero)
+        cb.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    st = cb.stats()
+    cb.set_chunk(32768)
+    sfc.deinit()
+    return {"workload": f"BASELINE config 3: 2048x2048 RGBA8, {n_strokes} strokes (round / miter joins, round caps, half dashed)", "ms_per_step": ms,
+            "strokes_per_s": scene.n / (ms * 1e-3), "mpix_s": st["covered_px"] / (ms * 1e-3) / 1e6,
+            "stages_ms": {k: st[k] for k in ("ms_flatten", "ms_bin", "ms_lists", "ms_raster", "ms_total")},
+            "counters": {k: int(st[k]) for k in ("edges", "band_edges", "tile_pairs", "crossings", "covered_px")}}

@@ -2,7 +2,7 @@
 # the dominant kernels, exported to CSV (the .ncu-rep files are too large to bring back).  tools/summarise_profile.py <tag>
 # turns the CSVs into profiles/<tag>_*.json.
 set -x
-B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c5 --chunk 0"
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c5 --no-extras --chunk 0"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c3.csv $B --workload c3 > gpurun_out/ncu_launches_c3.log 2>&1
 cap() {  # kernel regex, tag, launches to skip, command...
