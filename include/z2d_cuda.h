@@ -300,6 +300,27 @@ typedef struct z2d_draw_cmd {
 } z2d_draw_cmd;
 int32_t z2d_submit(z2d_ctx* ctx, const z2d_draw_cmd* cmds, size_t n, int32_t* statuses);
 
+/* ---- text runs from device-resident glyph outlines (text.show, src/text.zig:73-195).
+ * text.show builds ONE path for a run: per glyph it sets the path transformation to translate(x + advance + pp1, y).scale(s, s)
+ * (text.zig:165-172) and replays the glyph's outline through Path.moveTo / lineTo / curveTo / close (Glyph.Outline.appendToPath,
+ * src/internal/Glyph.zig:845-869), i.e. every outline point goes through Transformation.userToDevice
+ * (src/Transformation.zig:194-206), and fills the result.  Here the outline is uploaded ONCE per glyph and the per-point
+ * transformation runs on the device with the same two multiplies and two adds in the same order, so a run costs 56 bytes per
+ * GLYPH of host work and upload instead of 56 bytes per NODE:
+ *   z2d_glyph_cache_add   `nodes` = what appendToPath produces under the identity transformation: closed sub-paths, each
+ *                         close_path followed by the move_to Path.close leaves behind (src/Path.zig:453-476); coordinates
+ *                         already clamped as Path does.  Errors as painter.fill (PathNotClosed, InvalidState).
+ *   z2d_fill_glyphs       one painter.fill whose node list is the concatenation, in order, of the cached outlines
+ *                         transformed by m = {ax, by, cx, dy, tx, ty}; options and errors as z2d_fill. */
+typedef struct z2d_glyph_instance {
+  uint32_t glyph; /* id returned by z2d_glyph_cache_add */
+  uint32_t _pad;
+  double m[6];
+} z2d_glyph_instance; /* 56 bytes */
+int32_t z2d_glyph_cache_add(z2d_ctx* ctx, const z2d_node* nodes, size_t n_nodes, uint32_t* glyph_out);
+int32_t z2d_fill_glyphs(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern, const z2d_glyph_instance* glyphs, size_t n_glyphs,
+                        const z2d_fill_opts* opts);
+
 /* Re-executes the device pipeline of the most recently flushed batch from its
  * device-resident inputs (nodes, draw table); nothing is read from the host.
  * Benchmarking aid: separates kernel time from host recording and H2D copies. */

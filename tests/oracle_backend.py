@@ -115,6 +115,34 @@ class OracleBackend:
     def stroke(self, hd, pat, nodes, n, opts):
         return self.lib.z2d_ref_stroke(hd.ptr, hd.fmt, hd.w, hd.h, C.byref(pat), nodes, n, C.byref(opts))
 
+    # text runs: the oracle has no glyph cache -- the outlines are kept on the host and expanded with Transformation.userToDevice
+    # (a.ax * x + a.by * y, then + a.tx: Transformation.zig:194-206) into an ordinary node list, as text.show does
+    def glyph_cache_add(self, nodes, n):
+        if not hasattr(self, "_glyphs"):
+            self._glyphs = []
+        self._glyphs.append([(nodes[i].tag, tuple(nodes[i].p)) for i in range(n)])
+        return len(self._glyphs) - 1
+
+    def fill_glyphs(self, hd, pat, instances, n, opts):
+        out = []
+        for i in range(n):
+            m = instances[i].m
+            for tag, p in self._glyphs[instances[i].glyph]:
+                q = [0.0] * 6
+                for k in range({0: 1, 1: 1, 2: 3, 3: 0}[tag]):
+                    x, y = p[2 * k], p[2 * k + 1]
+                    dx, dy = m[0] * x + m[1] * y, m[2] * x + m[3] * y
+                    q[2 * k], q[2 * k + 1] = dx + m[4], dy + m[5]
+                out.append((tag, q))
+        if not out:
+            return 0
+        arr = (abi.Node * len(out))()
+        for i, (tag, q) in enumerate(out):
+            arr[i].tag = tag
+            for k in range(6):
+                arr[i].p[k] = q[k]
+        return self.fill(hd, pat, arr, len(out), opts)
+
     def composite(self, hd, dst_x, dst_y, ops, n, precision):
         return self.lib.z2d_ref_composite(hd.ptr, hd.fmt, hd.w, hd.h, dst_x, dst_y, ops, n, precision)
 

@@ -7,7 +7,7 @@ from the reference's spec/test-fonts by tests/golden/import_goldens.py)."""
 import os
 import struct
 
-from z2d_b200.host import FillOptions, Path, Transformation, painter
+from z2d_b200.host import FillOptions, Path, Transformation, nodes_to_array, painter
 
 FONT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "fonts")
 
@@ -426,5 +426,71 @@ def text_nodes(font, text, x, y, size, transformation=None):
     return path.nodes
 
 
+_GLYPH_CACHES = None  # dict (backend id, font id) -> GlyphCache while use_glyph_cache(True): show_text goes through z2d_fill_glyphs
+
+
+def use_glyph_cache(on):
+    """Route show_text through the backend's glyph cache (z2d_glyph_cache_add / z2d_fill_glyphs) instead of host-built node lists."""
+    global _GLYPH_CACHES
+    _GLYPH_CACHES = {} if on else None
+
+
 def show_text(surface, pattern, font, text, x, y, size, fill_opts=None, transformation=None):
+    if _GLYPH_CACHES is not None:
+        key = (id(surface.backend), id(font))
+        if key not in _GLYPH_CACHES:
+            _GLYPH_CACHES[key] = GlyphCache(surface.backend, font)
+        return show_text_cached(surface, pattern, font, text, x, y, size, _GLYPH_CACHES[key], fill_opts, transformation)
     painter.fill(surface, pattern, text_nodes(font, text, x, y, size, transformation), fill_opts or FillOptions())
+
+
+class GlyphCache:
+    """Per (backend, font): glyph outlines uploaded once (z2d_glyph_cache_add) in the form Outline.appendToPath produces under the
+    identity transformation, i.e. replayed through a Path so that Path.close's trailing move_to and the coordinate clamp are in."""
+
+    def __init__(self, backend, font):
+        self.backend, self.font, self.ids = backend, font, {}
+
+    def glyph_id(self, cp, outline):
+        if cp not in self.ids:
+            path = Path()
+            for n in outline["nodes"]:  # Outline.appendToPath
+                tag = int(n[0])
+                if tag == 0:
+                    path.move_to(n[1], n[2])
+                elif tag == 1:
+                    path.line_to(n[1], n[2])
+                elif tag == 2:
+                    path.curve_to(*n[1:7])
+                else:
+                    path.close()
+            self.ids[cp] = self.backend.glyph_cache_add(nodes_to_array(path.nodes), len(path.nodes))
+        return self.ids[cp]
+
+
+def show_text_cached(surface, pattern, font, text, x, y, size, cache, fill_opts=None, transformation=None):
+    """text.show with the glyph outlines resident in the backend: the host only computes one transformation per glyph
+    (text.zig:165-172) and the advance; the per-point work runs where the pixels are."""
+    glyphs, outlines, instances = {}, {}, []
+    base = transformation or Transformation()
+    cps = [ord(ch) for ch in text]
+    scale = size / float(font.units_per_em)
+    advance = 0.0
+
+    def get(cp):
+        if cp not in glyphs:
+            glyphs[cp] = font.glyph(cp)
+        return glyphs[cp]
+
+    for idx, cp in enumerate(cps):
+        g = get(cp)
+        nxt = get(cps[idx + 1]) if idx + 1 < len(cps) else None
+        if g["outline"] is not None:
+            if cp not in outlines:
+                outlines[cp] = font.outline(g)
+            o = outlines[cp]
+            pp1 = float(o["x_min"] - g["lsb"]) if not font.lsb_is_at_x_zero else 0.0
+            instances.append((cache.glyph_id(cp, o), base.translate(x + advance + pp1, y).scale(scale, scale)))
+        kern = float(font.kern_advance(g["index"], nxt["index"])) if nxt is not None else 0.0
+        advance += (float(g["advance"] if g["advance"] > 0 else font.advance_width_max) + kern) * scale
+    painter.fill_glyphs(surface, pattern, instances, fill_opts or FillOptions())

@@ -264,6 +264,10 @@ class CompOpPOD(C.Structure):
     _fields_ = [("op", C.c_uint32), ("dst", CompParamPOD), ("src", CompParamPOD)]
 
 
+class GlyphInstancePOD(C.Structure):
+    _fields_ = [("glyph", C.c_uint32), ("_pad", C.c_uint32), ("m", C.c_double * 6)]
+
+
 class StatsPOD(C.Structure):
     _fields_ = [("draws", C.c_uint64), ("nodes", C.c_uint64), ("edges", C.c_uint64), ("band_edges", C.c_uint64),
                 ("tile_items", C.c_uint64), ("tiles", C.c_uint64), ("covered_px", C.c_uint64), ("region_px", C.c_uint64),
@@ -280,6 +284,7 @@ class DrawCmdPOD(C.Structure):
 
 
 assert C.sizeof(Node) == 56
+assert C.sizeof(GlyphInstancePOD) == 56
 
 
 def surface_byte_len(fmt, w, h):

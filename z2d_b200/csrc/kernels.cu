@@ -1148,6 +1148,26 @@ void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* s
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {
   if (n_draws) k_edge_sim<<<blocks_for(n_draws, 64), 64, 0, st>>>(draws, n_draws, sfcs, edges, sp_off, perm, xs, rows);
 }
+// text.show on the device: one block per glyph instance, threads over the nodes of its cached outline; every point goes through
+// Transformation.userToDevice (Transformation.zig:194-206: ax * x + by * y, then + tx; no contraction) into the batch's node array.
+__global__ void __launch_bounds__(128) k_expand_glyphs(const GlyphInst* __restrict__ inst, const z2d_node* __restrict__ cache,
+                                                       z2d_node* __restrict__ nodes) {
+  const GlyphInst g = inst[blockIdx.x];
+  for (uint32_t k = threadIdx.x; k < g.n_nodes; k += blockDim.x) {
+    z2d_node nd = cache[g.src + k];
+    const int np = nd.tag == Z2D_NODE_CURVE_TO ? 3 : (nd.tag == Z2D_NODE_CLOSE_PATH ? 0 : 1);
+    for (int q = 0; q < np; q++) {
+      const double x = nd.p[2 * q], y = nd.p[2 * q + 1];
+      const double dx = g.m[0] * x + g.m[1] * y, dy = g.m[2] * x + g.m[3] * y;
+      nd.p[2 * q] = dx + g.m[4];
+      nd.p[2 * q + 1] = dy + g.m[5];
+    }
+    nodes[g.dst + k] = nd;
+  }
+}
+void launch_expand_glyphs(const GlyphInst* inst, uint32_t n, const z2d_node* cache, z2d_node* nodes, cudaStream_t st) {
+  if (n) k_expand_glyphs<<<n, 128, 0, st>>>(inst, cache, nodes);
+}
 void launch_small_batch(const SmallArgs& A, cudaStream_t st) { k_small_batch<<<1, kSmallThreads, 0, st>>>(A); }
 void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st) {
   if (!A.n_tiles) return;

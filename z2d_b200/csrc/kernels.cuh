@@ -77,6 +77,13 @@ void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const
 // exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);
+// ---- glyph instances of a text run (z2d_fill_glyphs): cached outline nodes [src, src + n_nodes) -> batch nodes [dst, ...)
+struct GlyphInst {
+  uint32_t src, n_nodes, dst, _pad;
+  double m[6];
+};
+void launch_expand_glyphs(const GlyphInst* inst, uint32_t n, const z2d_node* cache, z2d_node* nodes, cudaStream_t st);
+
 // ---- small batches in two launches (smallbatch.cuh)
 constexpr uint32_t kSmallMaxDraws = 64, kSmallMaxNodes = 4096, kSmallMaxSubPaths = 1024, kSmallMaxWork = 4096;
 constexpr uint32_t kSmallEdgeCap = 1u << 18, kSmallBandCap = 1u << 19, kSmallSlotCap = 1u << 14, kSmallItemCap = 1u << 14;

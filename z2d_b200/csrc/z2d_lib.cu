@@ -126,6 +126,7 @@ struct Batch {  // one recorded command batch (host side)
   std::vector<DevGrad> grads;
   std::vector<float> stop_offsets;
   std::vector<float4> stop_colors;
+  std::vector<GlyphInst> ginst;  // glyph instances of the batch's text runs (z2d_fill_glyphs): expanded into `nodes` on the device
   std::vector<double> dashes;   // concatenated dash arrays of the batch's dashed strokes
   std::vector<double> pens;     // pen vertices, 6 doubles each {px,py,cw.dx,cw.dy,ccw.dx,ccw.dy}
   double pen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // parameters of the most recently built pen (thickness, tolerance, ctm)
@@ -147,6 +148,7 @@ struct InputSet {  // device copies of one batch's uploaded inputs; two sets, so
   const float4* stop_col = nullptr;
   const void* pens = nullptr;
   const double* dashes = nullptr;
+  const GlyphInst* ginst = nullptr;
   cudaEvent_t done = nullptr;  // recorded on the main stream after the last kernel that reads this set
   bool used = false;
   void release() {
@@ -193,6 +195,15 @@ struct z2d_ctx {
   DevBuf d_counters, d_boxes, d_hots, d_band_hdr, d_band_xr;
   DevBuf d_export, d_gamma;  // z2d_surface_export: scanline staging, sRGB channel table
   DevBuf d_sim_rows, d_sim_perm, d_sim_x;  // k_edge_sim: row records, per-edge scratch
+  // glyph cache (z2d_glyph_cache_add): outlines in Path space, host mirror + device copy; per glyph its node range and sub-paths
+  struct GlyphEntry {
+    uint32_t node_off, n_nodes, sp_off, n_sp;
+  };
+  std::vector<z2d_node> glyph_nodes;
+  std::vector<DevSubPath> glyph_sps;  // node_begin / node_end relative to the glyph
+  std::vector<GlyphEntry> glyphs;
+  DevBuf d_glyph_nodes;
+  size_t glyph_nodes_on_device = 0;
   DevBuf d_small_out;                      // small-batch path: the prepare kernel's result block (abort flag, totals)
   uint32_t* h_small = nullptr;             // its pinned host copy
   bool small_pending = false;              // a small batch is on the stream and its abort flag has not been looked at yet
@@ -491,6 +502,7 @@ void clear_batch(z2d_ctx* c, Batch& B) {
   B.stop_offsets.clear();
   B.stop_colors.clear();
   B.dashes.clear();
+  B.ginst.clear();
   B.pens.clear();
   B.pen_cached = false;
 }
@@ -879,11 +891,12 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   //    The small tables travel as one pinned blob (sections 256-byte aligned) with typed device pointers into it.
   InputSet& S = c->in[B.index];
   struct Sec { const void* src; size_t bytes; size_t off; };
-  Sec sec[10] = {{B.strokes.data(), B.strokes.size() * sizeof(StrokeIn), 0}, {B.srcs.data(), B.srcs.size() * sizeof(DevSrc), 0},
+  Sec sec[11] = {{B.strokes.data(), B.strokes.size() * sizeof(StrokeIn), 0}, {B.srcs.data(), B.srcs.size() * sizeof(DevSrc), 0},
                  {sfcs.data(), sfcs.size() * sizeof(DevSurface), 0},         {work_base.data(), work_base.size() * 4, 0},
                  {chunk_base.data(), chunk_base.size() * 4, 0},             {B.grads.data(), B.grads.size() * sizeof(DevGrad), 0},
                  {B.stop_offsets.data(), B.stop_offsets.size() * 4, 0},     {B.stop_colors.data(), B.stop_colors.size() * sizeof(float4), 0},
-                 {B.pens.data(), B.pens.size() * 8, 0},                     {B.dashes.data(), B.dashes.size() * 8, 0}};
+                 {B.pens.data(), B.pens.size() * 8, 0},                     {B.dashes.data(), B.dashes.size() * 8, 0},
+                 {B.ginst.data(), B.ginst.size() * sizeof(GlyphInst), 0}};
   size_t side_bytes = 0;
   for (Sec& x : sec) {
     x.off = side_bytes;
@@ -918,9 +931,20 @@ int flush_impl(z2d_ctx* c, Batch& B) {
     S.stop_col = reinterpret_cast<const float4*>(base + sec[7].off);
     S.pens = base + sec[8].off;
     S.dashes = reinterpret_cast<const double*>(base + sec[9].off);
+    S.ginst = reinterpret_cast<const GlyphInst*>(base + sec[10].off);
   }
   CK(c, cudaEventRecord(c->ev_up, c->copy_stream));
   CK(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+  if (!B.ginst.empty()) {  // text runs: the device writes the transformed outline nodes into the uploaded node array
+    if (c->glyph_nodes_on_device != c->glyph_nodes.size()) {
+      CK(c, c->d_glyph_nodes.ensure(c->glyph_nodes.size() * sizeof(z2d_node) + 64));
+      CK(c, cudaMemcpyAsync(c->d_glyph_nodes.p, c->glyph_nodes.data(), c->glyph_nodes.size() * sizeof(z2d_node), cudaMemcpyHostToDevice, st));
+      CK(c, cudaStreamSynchronize(st));  // (pageable source: the copy is staged; the sync only closes the race with a later add)
+      c->glyph_nodes_on_device = c->glyph_nodes.size();
+    }
+    launch_expand_glyphs(S.ginst, (uint32_t)B.ginst.size(), c->d_glyph_nodes.as<z2d_node>(), S.d_nodes.as<z2d_node>(), st);
+    CK(c, cudaGetLastError());
+  }
   BatchMeta& m = c->last;
   m.valid = true;
   m.set = B.index;
@@ -1236,6 +1260,7 @@ void z2d_ctx_destroy(z2d_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   c->d_export.release();
   c->d_gamma.release();
+  c->d_glyph_nodes.release();
   c->d_small_out.release();
   if (c->h_small) cudaFreeHost(c->h_small);
   c->d_sim_rows.release();
@@ -1709,6 +1734,102 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   if (c->chunk_draws && c->rec->draws.n >= kMinChunkDraws &&
       (c->rec->draws.n >= c->chunk_draws || !c->busy.load(std::memory_order_relaxed)))
     return kick(c);
+  return Z2D_OK;
+}
+
+int32_t z2d_glyph_cache_add(z2d_ctx* c, const z2d_node* nodes, size_t n, uint32_t* out) {
+  if (!c || !out || (n && !nodes)) return Z2D_E_INVALID_ARG;
+  if (n == 0) {  // a glyph without outline (whitespace): an entry that expands to nothing
+    c->glyphs.push_back({(uint32_t)c->glyph_nodes.size(), 0u, (uint32_t)c->glyph_sps.size(), 0u});
+    *out = (uint32_t)c->glyphs.size() - 1;
+    return Z2D_OK;
+  }
+  if (!is_closed_node_set(nodes, n)) return Z2D_E_PATH_NOT_CLOSED;  // painter.zig:82 on the run this glyph would be part of
+  if (nodes[0].tag != Z2D_NODE_MOVE_TO) return Z2D_E_INVALID_STATE;  // (outlines start with a move_to: fill_plotter.zig:50,53)
+  uint32_t n_sp = 0, n_par = 0;
+  int rc = split_subpaths(nodes, n, 0, 0, false, nullptr, n_sp, n_par);
+  if (rc) return rc;
+  const size_t sp0 = c->glyph_sps.size();
+  c->glyph_sps.resize(sp0 + n_sp);
+  split_subpaths(nodes, n, 0, 0, false, c->glyph_sps.data() + sp0, n_sp, n_par);
+  c->glyphs.push_back({(uint32_t)c->glyph_nodes.size(), (uint32_t)n, (uint32_t)sp0, n_sp});
+  c->glyph_nodes.insert(c->glyph_nodes.end(), nodes, nodes + n);
+  *out = (uint32_t)c->glyphs.size() - 1;
+  return Z2D_OK;
+}
+
+int32_t z2d_fill_glyphs(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d_glyph_instance* gi, size_t n, const z2d_fill_opts* o) {
+  if (!c || !s || !pattern || !o || s->ctx != c || (n && !gi)) return Z2D_E_INVALID_ARG;
+  if (o->op >= Z2D_OP_COUNT || o->fill_rule > 1 || o->precision > 1 || o->anti_aliasing_mode > Z2D_AA_SUPERSAMPLE_4X) return Z2D_E_INVALID_ARG;
+  if (pattern->kind == Z2D_PATTERN_OPAQUE && !px_can_demultiply(pattern->pixel)) return Z2D_E_PIXEL_SOURCE_NOT_PREMULTIPLIED;
+  size_t total = 0, total_sp = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (gi[i].glyph >= c->glyphs.size()) return Z2D_E_INVALID_ARG;
+    total += c->glyphs[gi[i].glyph].n_nodes;
+    total_sp += c->glyphs[gi[i].glyph].n_sp;
+  }
+  if (total == 0) return Z2D_OK;  // painter.zig:81: an empty node list is a no-op
+  DevDraw d;
+  memset(&d, 0, sizeof d);
+  uint32_t aa = (s->fmt == Z2D_FMT_ALPHA1) ? (uint32_t)Z2D_AA_NONE : o->anti_aliasing_mode;
+  if (aa == Z2D_AA_DEFAULT) aa = Z2D_AA_MULTISAMPLE_4X;
+  d.aa = aa;
+  d.rule = o->fill_rule;
+  d.op = o->op;
+  d.precision = op_requires_float(o->op) ? (uint32_t)Z2D_PRECISION_FLOAT : o->precision;
+  d.tolerance = o->tolerance > 0.001 ? o->tolerance : 0.001;
+  if (aa == Z2D_AA_NONE && !op_is_bounded(o->op)) d.mode = 2;
+  Batch& B = *c->rec;
+  const size_t save_g = B.grads.size(), save_o = B.stop_offsets.size(), save_c = B.stop_colors.size();
+  int rc = pattern_to_src(*pattern, d.src, B.grads, B.stop_offsets, B.stop_colors);
+  if (rc) return rc;
+  const uint32_t surface = batch_slot(c, s);
+  const uint32_t reduces = (d.src.kind == Z2D_PARAM_PIXEL && (d.op == Z2D_OP_SRC || (d.op == Z2D_OP_SRC_OVER && px_is_opaque(pattern->pixel)))) ? 1u : 0u;
+  const uint32_t paint_raw = d.src.kind == Z2D_PARAM_PIXEL
+                                 ? pixel_to_raw(s->fmt, pattern->pixel.format, pattern->pixel.r, pattern->pixel.g, pattern->pixel.b, pattern->pixel.a)
+                                 : 0u;
+  const size_t node0 = B.nodes.n, sp0 = B.subpaths.n;
+  if (!B.nodes.reserve(node0 + total) || !B.subpaths.reserve(sp0 + total_sp)) {
+    B.grads.resize(save_g); B.stop_offsets.resize(save_o); B.stop_colors.resize(save_c);
+    return Z2D_E_OUT_OF_MEMORY;
+  }
+  memset(B.nodes.p + node0, 0, total * sizeof(z2d_node));  // (overwritten on the device by k_expand_glyphs)
+  const uint32_t di = (uint32_t)B.draws.n;
+  size_t at = node0, sp_at = sp0;
+  for (size_t i = 0; i < n; i++) {
+    const z2d_ctx::GlyphEntry& g = c->glyphs[gi[i].glyph];
+    if (!g.n_nodes) continue;
+    GlyphInst gx;
+    gx.src = g.node_off; gx.n_nodes = g.n_nodes; gx.dst = (uint32_t)at; gx._pad = 0;
+    for (int k = 0; k < 6; k++) gx.m[k] = gi[i].m[k];
+    B.ginst.push_back(gx);
+    for (uint32_t k = 0; k < g.n_sp; k++) {  // every contour is plotted by the sequential fill plotter (exact for any transformation)
+      DevSubPath sp = c->glyph_sps[g.sp_off + k];
+      sp.draw = di;
+      sp.node_begin += (uint32_t)at;
+      sp.node_end += (uint32_t)at;
+      sp.flags = 0;
+      B.subpaths.p[sp_at++] = sp;
+    }
+    at += g.n_nodes;
+  }
+  if (sp_at > sp0) B.subpaths.p[sp_at - 1].flags |= kSpLastOfDraw;
+  B.nodes.n = at;
+  B.subpaths.n = sp_at;
+  DrawIn in;
+  in.surface = surface;
+  in.opts = pack_draw_opts(0, d.aa, d.rule, d.op, d.precision, reduces, d.mode);
+  in.paint_raw = paint_raw;
+  in.px_rgba = d.src.px_rgba;
+  in.tolerance = d.tolerance;
+  in.src_index = kNoIndex;
+  in.stroke_index = kNoIndex;
+  if (d.src.kind != Z2D_PARAM_PIXEL) {
+    in.src_index = (uint32_t)B.srcs.size();
+    B.srcs.push_back(d.src);
+  }
+  if (!B.draws.push(in)) return Z2D_E_OUT_OF_MEMORY;
+  if (B.nodes.n > kMaxBatchNodes || B.draws.n > kMaxBatchDraws) return flush(c);
   return Z2D_OK;
 }
 

@@ -64,6 +64,8 @@ def load_library():
         "z2d_composite": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, P(abi.CompOpPOD), C.c_size_t, C.c_uint32]),
         "z2d_submit": (C.c_int32, [vp, P(abi.DrawCmdPOD), C.c_size_t, P(C.c_int32)]),
         "z2d_replay": (C.c_int32, [vp]),
+        "z2d_glyph_cache_add": (C.c_int32, [vp, P(abi.Node), C.c_size_t, P(C.c_uint32)]),
+        "z2d_fill_glyphs": (C.c_int32, [vp, vp, P(abi.PatternPOD), P(abi.GlyphInstancePOD), C.c_size_t, P(abi.FillOptsPOD)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -77,7 +79,7 @@ EXPORTED_SYMBOLS = ["z2d_version", "z2d_last_error", "z2d_ctx_create", "z2d_ctx_
                     "z2d_get_stats", "z2d_surface_create", "z2d_surface_create_band", "z2d_surface_band", "z2d_surface_band_view", "z2d_surface_ipc_export", "z2d_surface_open_peer_band", "z2d_surface_destroy", "z2d_surface_byte_len",
                     "z2d_surface_width", "z2d_surface_height", "z2d_surface_format", "z2d_surface_upload",
                     "z2d_surface_download", "z2d_surface_download_async", "z2d_surface_device_ptr", "z2d_surface_export_size", "z2d_surface_export", "z2d_surface_paint_pixel", "z2d_surface_downsample",
-                    "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay"]
+                    "z2d_surface_put_pixel", "z2d_surface_get_pixel", "z2d_fill", "z2d_stroke", "z2d_composite", "z2d_submit", "z2d_replay", "z2d_glyph_cache_add", "z2d_fill_glyphs"]
 
 
 class CudaBackend:
@@ -193,6 +195,17 @@ class CudaBackend:
 
     def composite(self, hd, dst_x, dst_y, ops, n, precision):
         rc = self.lib.z2d_composite(self.ctx, hd, dst_x, dst_y, ops, n, precision)
+        if rc == abi.E_DEVICE:
+            raise abi.DeviceError(self.lib.z2d_last_error(self.ctx).decode())
+        return rc
+
+    def glyph_cache_add(self, nodes, n):
+        out = C.c_uint32()
+        self._check(self.lib.z2d_glyph_cache_add(self.ctx, nodes, n, C.byref(out)))
+        return out.value
+
+    def fill_glyphs(self, hd, pat, instances, n, opts):
+        rc = self.lib.z2d_fill_glyphs(self.ctx, hd, C.byref(pat), instances, n, C.byref(opts))
         if rc == abi.E_DEVICE:
             raise abi.DeviceError(self.lib.z2d_last_error(self.ctx).decode())
         return rc

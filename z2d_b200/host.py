@@ -751,6 +751,19 @@ class painter:
         abi.check(surface.backend.fill(surface.handle, pat, arr, len(nodes), opts.pod()))
 
     @staticmethod
+    def fill_glyphs(surface, pattern, instances, opts=None):
+        """One painter.fill of a text run whose glyph outlines live in the backend's glyph cache: instances = [(glyph id,
+        Transformation), ...] in run order (text.show, text.zig:73-195; z2d_fill_glyphs)."""
+        opts = opts or FillOptions()
+        arr = (abi.GlyphInstancePOD * max(1, len(instances)))()
+        for i, (gid, tr) in enumerate(instances):
+            arr[i].glyph = int(gid)
+            for k, v in enumerate(tr.as_tuple()):
+                arr[i].m[k] = v
+        pat = pattern.pod()
+        abi.check(surface.backend.fill_glyphs(surface.handle, pat, arr, len(instances), opts.pod()))
+
+    @staticmethod
     def stroke(surface, pattern, nodes, opts=None):
         opts = opts or StrokeOptions()
         arr = nodes_to_array(nodes)
