@@ -85,134 +85,9 @@ void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp
 // =====================================================================================
 // K1: flatten (fill) -- thread per sub-path
 // =====================================================================================
-struct Pt {
-  double x, y;
-};
-Z2D_D bool pt_eq(Pt a, Pt b) { return a.x == b.x && a.y == b.y; }
-
-struct Knots {
-  Pt a, b, c, d;
-};
-
-Z2D_D double knots_error_sq(const Knots& k) {  // tess/Spline.zig:83-123
-  double bx = k.b.x - k.a.x, by = k.b.y - k.a.y, cx = k.c.x - k.a.x, cy = k.c.y - k.a.y;
-  if (k.a.x != k.d.x || k.a.y != k.d.y) {
-    double dx = k.d.x - k.a.x, dy = k.d.y - k.a.y;
-    double dd = dx * dx + dy * dy;
-    double bd = bx * dx + by * dy;
-    if (bd >= dd) {
-      bx -= dx;
-      by -= dy;
-    } else {
-      bx -= bd / dd * dx;
-      by -= bd / dd * dy;
-    }
-    double cd = cx * dx + cy * dy;
-    if (cd >= dd) {
-      cx -= dx;
-      cy -= dy;
-    } else {
-      cx -= cd / dd * dx;
-      cy -= cd / dd * dy;
-    }
-  }
-  double be = bx * bx + by * by, ce = cx * cx + cy * cy;
-  return be > ce ? be : ce;
-}
-Z2D_D Pt lerp_half(Pt a, Pt b) { return {a.x + ((b.x - a.x) / 2), a.y + ((b.y - a.y) / 2)}; }
-Z2D_D Knots knots_split(Knots& k) {  // tess/Spline.zig:128-151 (k becomes the first half)
-  Pt ab = lerp_half(k.a, k.b), bc = lerp_half(k.b, k.c), cd = lerp_half(k.c, k.d);
-  Pt abbc = lerp_half(ab, bc), bccd = lerp_half(bc, cd);
-  Pt fin = lerp_half(abbc, bccd);
-  Knots r{fin, bccd, cd, k.d};
-  k.b = ab;
-  k.c = abbc;
-  k.d = fin;
-  return r;
-}
-
-// Edge sink: applies Polygon.addEdge (tess/Polygon.zig:61-109).  EMIT=false counts and tracks extents.
-template <bool EMIT>
-struct EdgeSink {
-  bool unpaired = false;
-  double scale;
-  uint32_t n = 0;
-  double top = 0, bottom = 0, left = 0, right = 0;
-  DevEdge* out = nullptr;
-  uint32_t* out_draw = nullptr;
-  uint32_t draw = 0;
-  uint32_t limit = 0xffffffffu;  // emit pass: number of edges the count pass found for this sink
-  // The plotters emit a contour's edges as its points arrive.  Where the reference throws an unfinished contour away (its points
-  // were only buffered), the edges emitted since a mark are taken back: count and extents in the count pass, the write position
-  // in the emit pass.
-  struct Mark {
-    uint32_t n;
-    double top, bottom, left, right;
-  };
-  Z2D_D Mark mark() const { return Mark{n, top, bottom, left, right}; }
-  Z2D_D void rewind(const Mark& m) {
-    n = m.n;
-    top = m.top;
-    bottom = m.bottom;
-    left = m.left;
-    right = m.right;
-  }
-  Z2D_D void add(Pt p0, Pt p1) {
-    double ax = p0.x * scale, ay = p0.y * scale, bx = p1.x * scale, by = p1.y * scale;
-    DevEdge e;
-    if (ay < by) {
-      e = {ay, by, ax, (bx - ax) / (by - ay)};
-    } else if (ay > by) {
-      e = {ay, by, bx, (ax - bx) / (ay - by)};
-    } else {
-      return;
-    }
-    if (EMIT) {
-      // positions at or beyond the count pass's total are always taken back by a later rewind(): never touch the slots of the
-      // next sub-path, which another thread is writing
-      if (n < limit) {
-        out[n] = e;
-        out_draw[n] = draw;
-      }
-    } else {
-      double t = ay < by ? ay : by, b = ay < by ? by : ay;
-      double l = ax < bx ? ax : bx, r = ax < bx ? bx : ax;
-      if (n == 0) {
-        top = t; bottom = b; left = l; right = r;
-      } else {
-        if (t < top) top = t;
-        if (b > bottom) bottom = b;
-        if (l < left) left = l;
-        if (r > right) right = r;
-      }
-    }
-    n++;
-  }
-};
-
-constexpr int kSplineStack = 48;
-
-// Iterative Spline.decompose (tess/Spline.zig:37-71): depth first, left half first; emits the START point of every accepted
-// piece except the very first, then the end point.  Only right halves are stacked (the left half stays in registers), which
-// keeps the local-memory traffic of the flatten kernels to one 64-byte store per split and one load per emitted point.
-template <class F>
-Z2D_D void spline_decompose(Pt a, Pt b, Pt c, Pt d, double tol_sq, F&& line_to) {
-  if (pt_eq(a, b) && pt_eq(c, d)) {  // Spline.zig:39-42
-    line_to(d);
-    return;
-  }
-  Knots stack[kSplineStack];
-  int sp = 0;
-  Knots k{a, b, c, d};
-  #pragma unroll 1
-  for (;;) {
-    while (!(knots_error_sq(k) < tol_sq || sp >= kSplineStack - 2)) stack[sp++] = knots_split(k);  // k becomes the left half
-    if (!pt_eq(k.a, a)) line_to(k.a);
-    if (sp == 0) break;
-    k = stack[--sp];
-  }
-  line_to(d);
-}
+}  // namespace z2d
+#include "geom.cuh"
+namespace z2d {
 
 // fill_plotter.plot (tess/fill_plotter.zig:21-97) restricted to one sub-path
 // (the plotter state resets at every move_to).
@@ -262,6 +137,7 @@ Z2D_D void fill_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint
 
 }  // namespace z2d
 #include "stroke.cuh"
+#include "stroke_units.cuh"
 namespace z2d {
 
 #ifndef Z2D_FLATTEN_THREADS
@@ -278,7 +154,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
   if (order) i = order[i];
   const DevSubPath sp = sps[i];
   if (i == 0 || sps[i - 1].draw != sp.draw) draws[sp.draw].sp_first = i;  // sub-paths of a draw are consecutive
-  if (sp.flags & kSpNodeParallel) {
+  if (sp.flags & (kSpNodeParallel | kSpStrokeUnits)) {
     sp_count[i] = 0;
     return;
   }
@@ -306,7 +182,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
   if (i >= n_sp) return;
   if (order) i = order[i];
   const DevSubPath sp = sps[i];
-  if (sp.flags & kSpNodeParallel) return;
+  if (sp.flags & (kSpNodeParallel | kSpStrokeUnits)) return;
   const DevDraw& d = draws[sp.draw];
   EdgeSink<true> sink;
   sink.scale = d.scale;
@@ -326,6 +202,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
 constexpr int kSpKeys = 1024;
 Z2D_D uint32_t sp_key(const DevSubPath& sp, const DevDraw* __restrict__ draws) {
   if (sp.flags & kSpNodeParallel) return 0;  // returns at once in the sequential kernels: keep them together at the end
+  // (kSpStrokeUnits sub-paths are keyed like every stroke: the walker's lanes diverge on dashed / node count as well)
   const DevDraw& d = draws[sp.draw];
   const uint32_t nn = min(sp.node_end - sp.node_begin, 15u);
   if (d.kind == 0) return 1 + nn;  // irregular fills
@@ -668,7 +545,9 @@ Z2D_D bool edge_band_range(const DevEdge& e, const DevDraw& d, int& t0, int& t1)
 
 Z2D_D void bin_count_edge(uint32_t i, const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, const DevDraw* __restrict__ draws,
                            uint32_t* __restrict__ band_count) {
-  const DevDraw& d = draws[edge_draw[i]];
+  const uint32_t di = edge_draw[i];
+  if (di == 0xffffffffu) return;  // dead pool slot (stroke_units.cuh)
+  const DevDraw& d = draws[di];
   if (!d.valid || d.mode == 2) return;
   int t0, t1;
   if (!edge_band_range(edges[i], d, t0, t1)) return;
@@ -684,7 +563,9 @@ __global__ void k_bin_count(const DevEdge* __restrict__ edges, const uint32_t* _
 Z2D_D void bin_scatter_edge(uint32_t i, const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, const DevDraw* __restrict__ draws,
                              const uint32_t* __restrict__ band_off, uint32_t* __restrict__ band_cursor, DevEdge* __restrict__ band_edges,
                              int4* __restrict__ band_hdr, uint2* __restrict__ band_xr, uint32_t band_cap) {
-  const DevDraw& d = draws[edge_draw[i]];
+  const uint32_t di = edge_draw[i];
+  if (di == 0xffffffffu) return;
+  const DevDraw& d = draws[di];
   if (!d.valid || d.mode == 2) return;
   const DevEdge e = edges[i];
   int t0, t1;
@@ -1099,6 +980,20 @@ void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* 
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st) {
   if (n_sp) k_flatten_emit<<<blocks_for(n_sp, Z2D_FLATTEN_THREADS), Z2D_FLATTEN_THREADS, 0, st>>>(sps, n_sp, nodes, draws, sp_off, edges, edge_draw, (const PenV*)pens, dashes, order);
+}
+void launch_stroke_units(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, const void* pens, const double* dashes,
+                         const uint32_t* order, void* units, uint32_t unit_cap, void* links, uint32_t link_cap, void* ports, uint32_t* ctr,
+                         DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap, cudaStream_t st) {
+  if (!n_sp) return;
+  cudaMemsetAsync(ctr, 0, 16, st);
+  k_stroke_walk<<<blocks_for(n_sp, 64), 64, 0, st>>>(sps, n_sp, nodes, draws, (const PenV*)pens, dashes, order, (StrokeUnit*)units, unit_cap,
+                                                     (StrokeLink*)links, link_cap, ctr);
+  if (unit_cap)
+    k_stroke_units<<<blocks_for(unit_cap, 128), 128, 0, st>>>((const StrokeUnit*)units, unit_cap, ctr, draws, (const PenV*)pens, dashes, (Pt*)ports,
+                                                              edges, edge_draw, edge_cap);
+  if (link_cap)
+    k_stroke_links<<<blocks_for(link_cap, 256), 256, 0, st>>>((const StrokeLink*)links, link_cap, unit_cap, ctr, draws, (const Pt*)ports, edges, edge_draw,
+                                                              edge_cap);
 }
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
                           DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,

@@ -59,6 +59,12 @@ void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* 
 void launch_sp_order(const DevSubPath* sps, uint32_t n_sp, const DevDraw* draws, uint32_t* keys_scratch, uint32_t* order, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st);
+// unit stroker (stroke_units.cuh) for the sub-paths flagged kSpStrokeUnits: walker -> units -> links.  ctr[0..2] = units, links and
+// edge slots taken (they run past the capacities when those are too small: the caller enlarges and repeats).
+constexpr size_t kStrokeUnitBytes = 64, kStrokeLinkBytes = 16, kStrokePortBytes = 64;  // per unit / link / unit
+void launch_stroke_units(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, DevDraw* draws, const void* pens, const double* dashes,
+                         const uint32_t* order, void* units, uint32_t unit_cap, void* links, uint32_t link_cap, void* ports, uint32_t* ctr,
+                         DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap, cudaStream_t st);
 // node-parallel flattening of the sub-paths flagged kSpNodeParallel: count pass (emit = false: also builds node_sp) / emit pass
 void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes,
                           DevDraw* draws, uint32_t* counts, const uint32_t* offs, DevEdge* edges, uint32_t* edge_draw,

@@ -300,6 +300,98 @@ struct SegIter {
   }
 };
 
+struct Dasher {  // tess/Dasher.zig
+  const double* d;
+  int n;
+  double offset;
+  int idx;
+  bool on;
+  double remain;
+  Z2D_D void reset() {
+    idx = 0;
+    on = true;
+    remain = d[0];
+    remain -= offset;
+    while (remain < 0 || remain > d[idx]) {
+      if (remain < 0) {
+        remain += d[idx];
+        idx = (idx >= n - 1) ? 0 : idx + 1;
+      } else {
+        remain -= d[idx];
+        idx = (idx == 0) ? n - 1 : idx - 1;
+      }
+      on = !on;
+    }
+  }
+  Z2D_D bool step(double len) {
+    remain -= len;
+    if (remain <= 0) {
+      on = !on;
+      idx += 1;
+      if (idx >= n) idx = 0;
+      remain = d[idx];
+      return true;
+    }
+    return false;
+  }
+};
+
+// ---- caps (Face.zig:154-284); `emit(p)` receives the cap points in order.  Written as one loop over "fixed head points, pen
+// vertices, fixed tail point" so that `emit` (which ends in the edge sink) is instantiated once per cap, not once per point.
+template <class F>
+Z2D_D void stroke_cap(const StrokeCtx& c, const Face& f, bool clockwise, F&& emit) {
+  Pt h0, h1, h2{}, h3{};
+  int n_head, idx = 0, end = 0;
+  bool tail = false;
+  switch (c.cap) {
+    case Z2D_CAP_BUTT:
+      n_head = 2;
+      h0 = clockwise ? f.p1_ccw : f.p1_cw;
+      h1 = clockwise ? f.p1_cw : f.p1_ccw;
+      break;
+    case Z2D_CAP_SQUARE: {
+      double ox = f.user.dx * f.half_width, oy = f.user.dy * f.half_width;
+      xf_dist(c.ctm, ox, oy);
+      n_head = 4;
+      h0 = clockwise ? f.p1_ccw : f.p1_cw;
+      h3 = clockwise ? f.p1_cw : f.p1_ccw;
+      h1 = {h0.x + ox, h0.y + oy};
+      h2 = {h3.x + ox, h3.y + oy};
+      break;
+    }
+    default:
+      n_head = 1;
+      h0 = clockwise ? f.p1_ccw : f.p1_cw;
+      h1 = clockwise ? f.p1_cw : f.p1_ccw;  // the tail point
+      tail = true;
+      pen_range(c, f.dev, Slope{-f.dev.dx, -f.dev.dy}, clockwise, idx, end);
+  }
+  #pragma unroll 1
+  for (int k = 0;;) {
+    Pt p;
+    if (k < n_head) {
+      p = k == 0 ? h0 : k == 1 ? h1 : k == 2 ? h2 : h3;
+      k++;
+    } else if (idx != end) {  // VertexIterator.next
+      const PenV v = c.pen[idx];
+      if (clockwise) {
+        idx += 1;
+        if (idx == c.npen) idx = 0;
+      } else {
+        if (idx == 0) idx = c.npen;
+        idx -= 1;
+      }
+      p = {f.p1.x + v.px, f.p1.y + v.py};
+    } else if (tail) {
+      p = h1;
+      tail = false;
+    } else {
+      break;
+    }
+    emit(p);
+  }
+}
+
 template <class Sink>
 struct Stroker {
   Sink& sink;
@@ -357,60 +449,9 @@ struct Stroker {
     ct.len = 0;
   }
 
-  // ---- caps (Face.zig:154-284); `emit(p)` receives the cap points in order.  Written as one loop over "fixed head points, pen
-  // vertices, fixed tail point" so that `emit` (which ends in the edge sink) is instantiated once per cap, not once per point.
   template <class F>
   Z2D_D void cap(const Face& f, bool clockwise, F&& emit) {
-    Pt h0, h1, h2{}, h3{};
-    int n_head, idx = 0, end = 0;
-    bool tail = false;
-    switch (c.cap) {
-      case Z2D_CAP_BUTT:
-        n_head = 2;
-        h0 = clockwise ? f.p1_ccw : f.p1_cw;
-        h1 = clockwise ? f.p1_cw : f.p1_ccw;
-        break;
-      case Z2D_CAP_SQUARE: {
-        double ox = f.user.dx * f.half_width, oy = f.user.dy * f.half_width;
-        xf_dist(c.ctm, ox, oy);
-        n_head = 4;
-        h0 = clockwise ? f.p1_ccw : f.p1_cw;
-        h3 = clockwise ? f.p1_cw : f.p1_ccw;
-        h1 = {h0.x + ox, h0.y + oy};
-        h2 = {h3.x + ox, h3.y + oy};
-        break;
-      }
-      default:
-        n_head = 1;
-        h0 = clockwise ? f.p1_ccw : f.p1_cw;
-        h1 = clockwise ? f.p1_cw : f.p1_ccw;  // the tail point
-        tail = true;
-        pen_range(c, f.dev, Slope{-f.dev.dx, -f.dev.dy}, clockwise, idx, end);
-    }
-    #pragma unroll 1
-    for (int k = 0;;) {
-      Pt p;
-      if (k < n_head) {
-        p = k == 0 ? h0 : k == 1 ? h1 : k == 2 ? h2 : h3;
-        k++;
-      } else if (idx != end) {  // VertexIterator.next
-        const PenV v = c.pen[idx];
-        if (clockwise) {
-          idx += 1;
-          if (idx == c.npen) idx = 0;
-        } else {
-          if (idx == 0) idx = c.npen;
-          idx -= 1;
-        }
-        p = {f.p1.x + v.px, f.p1.y + v.py};
-      } else if (tail) {
-        p = h1;
-        tail = false;
-      } else {
-        break;
-      }
-      emit(p);
-    }
+    stroke_cap(c, f, clockwise, emit);
   }
 
   // ---- stroke_plotter.join (stroke_plotter.zig:410-561); use_before: outer points are inserted
@@ -615,42 +656,6 @@ struct Stroker {
   }
 
   // =============================== dashed (dashed_plotter.zig)
-  struct Dasher {  // tess/Dasher.zig
-    const double* d;
-    int n;
-    double offset;
-    int idx;
-    bool on;
-    double remain;
-    Z2D_D void reset() {
-      idx = 0;
-      on = true;
-      remain = d[0];
-      remain -= offset;
-      while (remain < 0 || remain > d[idx]) {
-        if (remain < 0) {
-          remain += d[idx];
-          idx = (idx >= n - 1) ? 0 : idx + 1;
-        } else {
-          remain -= d[idx];
-          idx = (idx == 0) ? n - 1 : idx - 1;
-        }
-        on = !on;
-      }
-    }
-    Z2D_D bool step(double len) {
-      remain -= len;
-      if (remain <= 0) {
-        on = !on;
-        idx += 1;
-        if (idx >= n) idx = 0;
-        remain = d[idx];
-        return true;
-      }
-      return false;
-    }
-  };
-
   Z2D_D void plot_dotted_dashed(PlotState& st, Pt point, Slope slope) {  // dashed_plotter.zig:369-465 (always on the main state)
     if (c.cap == Z2D_CAP_ROUND) {
       pen_circle(st, point);
@@ -827,10 +832,8 @@ struct Stroker {
   }
 };
 
-template <bool EMIT>
-Z2D_D void stroke_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint32_t end, const DevDraw& d, const PenV* pens,
-                          const double* dashes, EdgeSink<EMIT>& sink) {
-  StrokeCtx c;
+#ifndef Z2D_HOST_TEST
+Z2D_D void stroke_ctx_of(StrokeCtx& c, const DevDraw& d, const PenV* pens, const double* dashes) {
   c.cap = d.cap;
   c.join = d.join;
   c.thickness = d.thickness;
@@ -848,9 +851,17 @@ Z2D_D void stroke_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, ui
   c.npen = (int)d.pen_count;
   c.dashes = dashes + d.dash_begin;
   c.ndash = (int)d.dash_count;
+}
+
+template <bool EMIT>
+Z2D_D void stroke_subpath(const z2d_node* __restrict__ nodes, uint32_t begin, uint32_t end, const DevDraw& d, const PenV* pens,
+                          const double* dashes, EdgeSink<EMIT>& sink) {
+  StrokeCtx c;
+  stroke_ctx_of(c, d, pens, dashes);
   sink.scale = 1.0;  // contour points are pre-scaled; the result polygon's own scale is 1
   Stroker<EdgeSink<EMIT>> s(sink, c);
   if (d.dash_count > 0) s.run_dashed(nodes, begin, end); else s.run_plain(nodes, begin, end);
 }
+#endif
 
 }  // namespace z2d

@@ -37,12 +37,14 @@ struct DevSurface {
 struct DevSubPath {  // one move_to ... run of nodes (state resets at every move_to)
   uint32_t draw;
   uint32_t node_begin, node_end;  // [begin,end) in the batch node array
-  uint32_t flags;                 // kSpLastOfDraw | kSpNodeParallel
+  uint32_t flags;                 // kSpLastOfDraw | kSpNodeParallel | kSpStrokeUnits
 };
 
 constexpr uint32_t kSpLastOfDraw = 1u;     // node_end is the end of the draw's node list
 constexpr uint32_t kSpNodeParallel = 2u;   // fill sub-path of the form move_to, segments..., close_path with >= 2 moving segments:
                                            // every node is flattened by its own thread (k_flatten_nodes)
+constexpr uint32_t kSpStrokeUnits = 4u;    // sub-path of an ordinary stroke: tessellated by the unit stroker (stroke_units.cuh), its
+                                           // edges go to the pool at the front of the edge array, not to a counted range
 
 struct DevDraw {
   // --- recorded on the host

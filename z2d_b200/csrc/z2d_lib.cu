@@ -42,6 +42,21 @@ struct DevBuf {  // growable device buffer
     if (e == cudaSuccess) cap = ncap;
     return e;
   }
+  // like ensure, but the first `keep` bytes survive a reallocation (device-to-device copy on `st`)
+  cudaError_t ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 4096;
+    while (ncap < bytes) ncap = ncap + ncap / 2 + 4096;
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (p) cudaFree(p);
+    p = np;
+    cap = ncap;
+    return e;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -99,7 +114,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0, n_srcs = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0, n_srcs = 0, n_unit_sp = 0;
   int set = 0;  // which InputSet holds the batch
   size_t n_nodes = 0, h2d_bytes = 0;
 };
@@ -122,6 +137,7 @@ struct Batch {  // one recorded command batch (host side)
   std::vector<DevSrc> srcs;
   uint32_t iso_mode = 0, iso_node_begin = 0, iso_node_end = 0;  // the isolated draw of a 1-draw batch
   uint32_t n_par_sp = 0;  // sub-paths flagged kSpNodeParallel
+  uint32_t n_unit_sp = 0; // sub-paths flagged kSpStrokeUnits
   std::vector<z2d_sfc*> batch_sfcs;
   std::vector<DevGrad> grads;
   std::vector<float> stop_offsets;
@@ -195,6 +211,11 @@ struct z2d_ctx {
   DevBuf d_counters, d_boxes, d_hots, d_band_hdr, d_band_xr;
   DevBuf d_export, d_gamma;  // z2d_surface_export: scanline staging, sRGB channel table
   DevBuf d_sim_rows, d_sim_perm, d_sim_x;  // k_edge_sim: row records, per-edge scratch
+  // unit stroker (stroke_units.cuh): unit / link records, port points, cursors; capacities in records, kept from batch to batch
+  DevBuf d_su_units, d_su_links, d_su_ports, d_su_ctr;
+  uint32_t su_unit_cap = 0, su_link_cap = 0, su_edge_cap = 0;
+  uint32_t last_scan_edges = 0;  // counted (non-pool) edges of the previous batch: sizes the edge array before the total is known
+  bool stroke_units = true;      // Z2D_NO_STROKE_UNITS=1: every stroke through the sub-path stroker
   // glyph cache (z2d_glyph_cache_add): outlines in Path space, host mirror + device copy; per glyph its node range and sub-paths
   struct GlyphEntry {
     uint32_t node_off, n_nodes, sp_off, n_sp;
@@ -493,6 +514,7 @@ void clear_batch(z2d_ctx* c, Batch& B) {
   B.subpaths.clear();
   B.draws.clear();
   B.n_par_sp = 0;
+  B.n_unit_sp = 0;
   B.strokes.clear();
   B.srcs.clear();
   (void)c;
@@ -544,6 +566,8 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     return cudaGetLastError();
   };
   NvtxRange r_batch("z2d batch");
+  int su_tries = 0;
+restart:
   nvtxRangePushA("z2d K0-K1 expand + flatten (count)");
   CK(c, c->d_counters.ensure(64));
   CK(c, cudaMemsetAsync(c->d_counters.p, 0, 64, st));
@@ -576,6 +600,26 @@ int run_pipeline(z2d_ctx* c, bool replay) {
     launches += 5;
   }
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
+  // K1 for ordinary strokes: the unit stroker writes its edges straight into the pool at the FRONT of the edge array, so the
+  // array is sized before the counted total is known (the previous batch's, corrected after the read-back below)
+  const bool units = m.n_unit_sp != 0;
+  if (units) {
+    if (c->su_unit_cap == 0) {
+      c->su_unit_cap = 4u * n_nodes + 4096u;
+      c->su_link_cap = 2u * c->su_unit_cap;
+      c->su_edge_cap = 16u * c->su_unit_cap;
+    }
+    CK(c, c->d_su_units.ensure((size_t)c->su_unit_cap * kStrokeUnitBytes));
+    CK(c, c->d_su_links.ensure((size_t)c->su_link_cap * kStrokeLinkBytes));
+    CK(c, c->d_su_ports.ensure((size_t)c->su_unit_cap * kStrokePortBytes));
+    CK(c, c->d_su_ctr.ensure(64));
+    CK(c, c->d_edges.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * sizeof(DevEdge) + 32));
+    CK(c, c->d_edge_draw.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * 4 + 16));
+    launch_stroke_units(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), S.pens, S.dashes, order,
+                        c->d_su_units.p, c->su_unit_cap, c->d_su_links.p, c->su_link_cap, c->d_su_ports.p, c->d_su_ctr.as<uint32_t>(),
+                        c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->su_edge_cap, st);
+    launches += 4;
+  }
 
   nvtxRangePop();
   nvtxRangePushA("z2d K2 setup + K3b list sizes + read-back");
@@ -596,33 +640,56 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 2, c->d_list_off.as<uint32_t>() + n_work, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 4, c->d_counters.as<unsigned long long>() + 4, 16, cudaMemcpyDeviceToHost, st));  // k_edge_sim sizes
+  if (units) CK(c, cudaMemcpyAsync(c->h_total + 8, c->d_su_ctr.p, 12, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
-  const uint32_t n_edges = c->h_total[0], n_slots = c->h_total[1], n_items = c->h_total[2];
+  uint32_t pool_edges = 0;
+  if (units) {
+    const uint32_t need_u = c->h_total[8], need_l = c->h_total[9], need_e = c->h_total[10];
+    if (need_u > c->su_unit_cap || need_l > c->su_link_cap || need_e > c->su_edge_cap) {
+      // a capacity was too small (first batch with strokes, or denser strokes than before): enlarge and redo the batch from its
+      // resident inputs.  When the unit array overflowed the edge need is only a lower bound, so this can take a second round.
+      if (++su_tries > 4) return fail(c, "stroke unit capacities", cudaErrorUnknown);
+      auto grow = [](uint32_t cap, uint32_t need) { return need > cap ? need + need / 8u + 1024u : cap; };
+      const bool units_lost = need_u > c->su_unit_cap;
+      c->su_unit_cap = grow(c->su_unit_cap, need_u);
+      c->su_link_cap = grow(c->su_link_cap, need_l);
+      c->su_edge_cap = grow(c->su_edge_cap, units_lost ? std::max(need_e, 12u * need_u) : need_e);
+      nvtxRangePop();
+      goto restart;
+    }
+    pool_edges = need_e;
+  }
+  const uint32_t n_scan_edges = c->h_total[0], n_slots = c->h_total[1], n_items = c->h_total[2];
+  const uint32_t n_edges = pool_edges + n_scan_edges;
+  c->last_scan_edges = n_scan_edges;
   const unsigned long long sim_rows = *reinterpret_cast<unsigned long long*>(c->h_total + 4),
                            sim_slots = *reinterpret_cast<unsigned long long*>(c->h_total + 6);
 
   nvtxRangePop();
   nvtxRangePushA("z2d K1 flatten (emit) + edge replay");
   // K1 (emit half)
-  CK(c, c->d_edges.ensure((size_t)n_edges * sizeof(DevEdge) + 32));
-  CK(c, c->d_edge_draw.ensure((size_t)n_edges * 4 + 16));
+  // (the pool part [0, pool_edges) is already written: a reallocation keeps it)
+  CK(c, c->d_edges.ensure_keep((size_t)n_edges * sizeof(DevEdge) + 32, (size_t)pool_edges * sizeof(DevEdge), st));
+  CK(c, c->d_edge_draw.ensure_keep((size_t)n_edges * 4 + 16, (size_t)pool_edges * 4, st));
+  DevEdge* const scan_edges = c->d_edges.as<DevEdge>() + pool_edges;  // counted ranges follow the pool
+  uint32_t* const scan_edge_draw = c->d_edge_draw.as<uint32_t>() + pool_edges;
   CK(c, c->d_list_items.ensure((size_t)n_items * sizeof(uint4) + 16));
   CK(c, c->d_band_xr.ensure((size_t)n_slots * sizeof(uint2) + 16));
   CK(c, c->d_band_count.ensure((size_t)n_slots * 4 + 16));
   CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
   launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
-                      c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), S.pens, S.dashes, order, st);
+                      scan_edges, scan_edge_draw, S.pens, S.dashes, order, st);
   if (par) {
     launch_flatten_nodes(true, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
-                         c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, c->d_edges.as<DevEdge>(),
-                         c->d_edge_draw.as<uint32_t>(), c->d_curve_list.as<uint32_t>(), st);
+                         c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, scan_edges,
+                         scan_edge_draw, c->d_curve_list.as<uint32_t>(), st);
     launches += 2;
   }
   if (sim_rows) {  // order-dependent draws (dangling edges, direct rasteriser with an unbounded operator): exact scanline replay
     CK(c, c->d_sim_rows.ensure((size_t)sim_rows * sizeof(int4)));
     CK(c, c->d_sim_perm.ensure((size_t)sim_slots * 4 + 16));
     CK(c, c->d_sim_x.ensure((size_t)sim_slots * 4 + 16));
-    launch_edge_sim(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, c->d_edges.as<DevEdge>(), c->d_sp_off.as<uint32_t>(),
+    launch_edge_sim(c->d_draws.as<DevDraw>(), n_draws, S.sfcs, scan_edges, c->d_sp_off.as<uint32_t>(),
                     c->d_sim_perm.as<uint32_t>(), c->d_sim_x.as<int32_t>(), c->d_sim_rows.as<int4>(), st);
     launches += 1;
   }
@@ -951,6 +1018,7 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.n_draws = n_draws;
   m.n_sp = n_sp;
   m.n_par_sp = B.n_par_sp;
+  m.n_unit_sp = B.n_unit_sp;
   m.n_strokes = (uint32_t)B.strokes.size();
   m.n_srcs = (uint32_t)B.srcs.size();
   m.n_sfc = n_sfc;
@@ -1229,6 +1297,7 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
   for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
   c->small_enabled = getenv("Z2D_NO_SMALL_BATCH") == nullptr;
+  c->stroke_units = getenv("Z2D_NO_STROKE_UNITS") == nullptr;
   if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&c->h_small, 32, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
       cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
     delete c;
@@ -1686,6 +1755,13 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
   const uint32_t di = (uint32_t)c->rec->draws.n;
   const uint32_t save_par = c->rec->n_par_sp;
   rc = record_nodes(c, di, nodes, n, d.kind == 0 && d.mode == 0, d.kind == 1 && d.dash_count > 0 && d.cap != Z2D_CAP_BUTT);
+  const uint32_t save_unit = c->rec->n_unit_sp;
+  if (rc == Z2D_OK && d.kind == 1 && d.mode == 0 && c->stroke_units) {
+    // ordinary strokes (not hairlines; not the direct rasteriser with an unbounded operator, whose result depends on the order
+    // of the call's edges): tessellated per join / cap by the unit stroker
+    for (size_t k = save_sp; k < c->rec->subpaths.n; k++) c->rec->subpaths.p[k].flags |= kSpStrokeUnits;
+    c->rec->n_unit_sp += (uint32_t)(c->rec->subpaths.n - save_sp);
+  }
   DrawIn in;
   in.surface = d.surface;
   in.opts = pack_draw_opts(d.kind, d.aa, d.rule, d.op, d.precision, d.reduces, d.mode);
@@ -1720,6 +1796,7 @@ static int32_t record_draw(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, c
     c->rec->nodes.n = save_nodes;
     c->rec->subpaths.n = save_sp;
     c->rec->n_par_sp = save_par;
+    c->rec->n_unit_sp = save_unit;
     c->rec->strokes.resize(save_st);
     c->rec->srcs.resize(save_src);
     c->rec->grads.resize(save_g);
