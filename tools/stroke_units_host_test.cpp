@@ -38,6 +38,62 @@ struct DevEdge {
 
 using namespace z2d;
 
+// Pen.vertexIteratorFor written the way the reference has it (Pen.zig:138-232): one copy of the two binary searches per
+// direction.  stroke.cuh merges the two copies into one loop; this is the yardstick for that rewrite.
+static int2 pen_range_reference(const PenV* __restrict__ v, int n, Slope from, Slope to, bool clockwise) {
+  int start = 0, end = 0;
+  auto cw = [&](int i) Z2D_LAMBDA { return Slope{v[i].cwx, v[i].cwy}; };
+  auto ccw = [&](int i) Z2D_LAMBDA { return Slope{v[i].ccwx, v[i].ccwy}; };
+  if (clockwise) {
+    int low = 0, high = n, i = (low + high) >> 1;
+    while (high - low > 1) {
+      if (slope_compare(cw(i), from) < 0) low = i; else high = i;
+      i = (low + high) >> 1;
+    }
+    if (slope_compare(cw(i), from) < 0) {
+      i += 1;
+      if (i == n) i = 0;
+    }
+    start = i;
+    if (slope_compare(to, ccw(i)) >= 0) {
+      low = i;
+      high = i + n;
+      i = (low + high) >> 1;
+      while (high - low > 1) {
+        const int j = i >= n ? i - n : i;
+        if (slope_compare(cw(j), to) > 0) high = i; else low = i;
+        i = (low + high) >> 1;
+      }
+      if (i >= n) i -= n;
+    }
+    end = i;
+  } else {
+    int low = 0, high = n, i = (low + high) >> 1;
+    while (high - low > 1) {
+      if (slope_compare(from, ccw(i)) < 0) low = i; else high = i;
+      i = (low + high) >> 1;
+    }
+    if (slope_compare(from, ccw(i)) < 0) {
+      i += 1;
+      if (i == n) i = 0;
+    }
+    start = i;
+    if (slope_compare(cw(i), to) <= 0) {
+      low = i;
+      high = i + n;
+      i = (low + high) >> 1;
+      while (high - low > 1) {
+        const int j = i >= n ? i - n : i;
+        if (slope_compare(to, ccw(j)) > 0) high = i; else low = i;
+        i = (low + high) >> 1;
+      }
+      if (i >= n) i -= n;
+    }
+    end = i;
+  }
+  return make_int2(max(0, start), max(0, end));
+}
+
 struct HostRec {
   std::vector<StrokeUnit> units;
   std::vector<StrokeLink> links;
@@ -246,6 +302,38 @@ int main(int argc, char** argv) {
     total_units += rec.units.size();
     total_links += rec.links.size();
   }
+  // ---- the merged pen search against the two-copy form
+  size_t pen_checks = 0;
+  for (int t = 0; t < 200000; t++) {
+    double m[6] = {1, 0, 0, 1, 0, 0};
+    if (t % 3 == 1) { m[0] = -1.5; m[1] = 0.3; m[2] = 0.2; m[3] = 1.1; }
+    if (t % 3 == 2) { m[0] = 2.0; m[3] = 0.5; }
+    std::vector<PenV> pen = make_pen(uni(0.3, 20.0), 0.1, m);
+    for (int k = 0; k < 8; k++) {
+      Slope from, to;
+      if (pick(3) == 0) {  // exactly along pen edges: the ties the searches are written around
+        const PenV& a = pen[pick((int)pen.size())];
+        const PenV& b = pen[pick((int)pen.size())];
+        from = pick(2) ? Slope{a.cwx, a.cwy} : Slope{a.ccwx, a.ccwy};
+        to = pick(2) ? Slope{b.cwx, b.cwy} : Slope{-from.dx, -from.dy};
+      } else {
+        from = Slope{uni(-1, 1), uni(-1, 1)};
+        to = pick(4) == 0 ? Slope{-from.dx, -from.dy} : Slope{uni(-1, 1), uni(-1, 1)};
+      }
+      if (pick(5) == 0) from.dx = 0;
+      if (pick(5) == 0) to.dy = 0;
+      for (int cwi = 0; cwi < 2; cwi++) {
+        const int2 a = pen_range_of(pen.data(), (int)pen.size(), from, to, cwi != 0);
+        const int2 b = pen_range_reference(pen.data(), (int)pen.size(), from, to, cwi != 0);
+        pen_checks++;
+        if (a.x != b.x || a.y != b.y) {
+          if (bad < 20) printf("pen_range mismatch: n %zu cw %d -> (%d,%d) vs (%d,%d)\n", pen.size(), cwi, a.x, a.y, b.x, b.y);
+          bad++;
+        }
+      }
+    }
+  }
+  printf("%zu pen searches compared\n", pen_checks);
   printf("%d cases, %zu edges, %zu units, %zu links: %d mismatches\n", n_cases, total_edges, total_units, total_links, bad);
   return bad ? 1 : 0;
 }

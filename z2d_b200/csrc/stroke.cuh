@@ -169,59 +169,39 @@ Z2D_D Pt face_intersect(const Face& in, const Face& out, bool clockwise) {  // F
   return {rx, ry};
 }
 
-// Pen.vertexIteratorFor (Pen.zig:138-232)
+// Pen.vertexIteratorFor (Pen.zig:138-232).  The reference has one copy of the two binary searches per direction; here the
+// direction only selects the operands and the sense of each Slope.compare (same calls, same operand order), so the lanes of a
+// warp that search clockwise and counter-clockwise run one loop together.
 Z2D_DN int2 pen_range_of(const PenV* __restrict__ v, int n, Slope from, Slope to, bool clockwise) {
-  int start = 0, end = 0;
   auto cw = [&](int i) Z2D_LAMBDA { return Slope{v[i].cwx, v[i].cwy}; };
   auto ccw = [&](int i) Z2D_LAMBDA { return Slope{v[i].ccwx, v[i].ccwy}; };
-  if (clockwise) {
-    int low = 0, high = n, i = (low + high) >> 1;
-    while (high - low > 1) {
-      if (slope_compare(cw(i), from) < 0) low = i; else high = i;
-      i = (low + high) >> 1;
-    }
-    if (slope_compare(cw(i), from) < 0) {
-      i += 1;
-      if (i == n) i = 0;
-    }
-    start = i;
-    if (slope_compare(to, ccw(i)) >= 0) {
-      low = i;
-      high = i + n;
-      i = (low + high) >> 1;
-      while (high - low > 1) {
-        const int j = i >= n ? i - n : i;
-        if (slope_compare(cw(j), to) > 0) high = i; else low = i;
-        i = (low + high) >> 1;
-      }
-      if (i >= n) i -= n;
-    }
-    end = i;
-  } else {
-    int low = 0, high = n, i = (low + high) >> 1;
-    while (high - low > 1) {
-      if (slope_compare(from, ccw(i)) < 0) low = i; else high = i;
-      i = (low + high) >> 1;
-    }
-    if (slope_compare(from, ccw(i)) < 0) {
-      i += 1;
-      if (i == n) i = 0;
-    }
-    start = i;
-    if (slope_compare(cw(i), to) <= 0) {
-      low = i;
-      high = i + n;
-      i = (low + high) >> 1;
-      while (high - low > 1) {
-        const int j = i >= n ? i - n : i;
-        if (slope_compare(to, ccw(j)) > 0) high = i; else low = i;
-        i = (low + high) >> 1;
-      }
-      if (i >= n) i -= n;
-    }
-    end = i;
+  // clockwise: compare(cw(i), from) < 0        counter-clockwise: compare(from, ccw(i)) < 0
+  auto before_from = [&](int i) Z2D_LAMBDA { return slope_compare(clockwise ? cw(i) : from, clockwise ? from : ccw(i)) < 0; };
+  int low = 0, high = n, i = (low + high) >> 1;
+  while (high - low > 1) {
+    if (before_from(i)) low = i; else high = i;
+    i = (low + high) >> 1;
   }
-  return make_int2(max(0, start), max(0, end));
+  if (before_from(i)) {
+    i += 1;
+    if (i == n) i = 0;
+  }
+  const int start = i;
+  // clockwise: compare(to, ccw(i)) >= 0        counter-clockwise: compare(cw(i), to) <= 0
+  const int r0 = slope_compare(clockwise ? to : cw(i), clockwise ? ccw(i) : to);
+  if (clockwise ? r0 >= 0 : r0 <= 0) {
+    low = i;
+    high = i + n;
+    i = (low + high) >> 1;
+    while (high - low > 1) {
+      const int j = i >= n ? i - n : i;
+      // clockwise: compare(cw(j), to) > 0      counter-clockwise: compare(to, ccw(j)) > 0
+      if (slope_compare(clockwise ? cw(j) : to, clockwise ? to : ccw(j)) > 0) high = i; else low = i;
+      i = (low + high) >> 1;
+    }
+    if (i >= n) i -= n;
+  }
+  return make_int2(max(0, start), max(0, i));
 }
 Z2D_D void pen_range(const StrokeCtx& c, Slope from, Slope to, bool clockwise, int& start_o, int& end_o) {
   const int2 r = pen_range_of(c.pen, c.npen, from, to, clockwise);

@@ -212,14 +212,20 @@ struct StrokeWalker {
   Z2D_D void run_dashed(const z2d_node* __restrict__ nodes, uint32_t begin, uint32_t end) {
     WState st, ist;
     PointBuf25 pts, ipts;
-    Slope cur_slope{0, 0}, islope{0, 0};
+    // current_slope (dashed_plotter.zig:98) is only read by a square dot: kept un-normalised, normalised where it is used
+    Slope cur_raw{0, 0}, iraw{0, 0};
+    bool cur_set = false, iset = false;
+    auto unit_slope = [&](Slope raw, bool set) Z2D_LAMBDA {
+      if (set && c.cap == Z2D_CAP_SQUARE) slope_normalize(raw);
+      return raw;
+    };
     int initial_kind = 0;  // 0 none, 1 off, 2 on
     Pt initial_off{0, 0};
     Dasher dasher{c.dashes, c.ndash, c.dash_offset, 0, true, 0.0};
     dasher.reset();
 
     auto emit_current = [&]() Z2D_LAMBDA {
-      if (pts.len == 1) plot_dotted_dashed(st, pts.first(), cur_slope);
+      if (pts.len == 1) plot_dotted_dashed(st, pts.first(), unit_slope(cur_raw, cur_set));
       else if (pts.len == 2) plot_single(st, pts.head(0), pts.head(1));
       else if (pts.len > 2) plot_open_joined(st, pts.head(0), pts.head(1), pts.tail(2), pts.tail(1));
     };
@@ -228,7 +234,8 @@ struct StrokeWalker {
         initial_kind = 2;
         ist = st;
         ipts = pts;
-        islope = cur_slope;
+        iraw = cur_raw;
+        iset = cur_set;
       } else {
         initial_kind = 1;
         initial_off = pts.first();
@@ -247,7 +254,7 @@ struct StrokeWalker {
     };
     auto finish_initial = [&]() Z2D_LAMBDA {
       if (ipts.len == 1) {
-        plot_dotted_dashed(st, ipts.first(), islope);
+        plot_dotted_dashed(st, ipts.first(), unit_slope(iraw, iset));
       } else if (ipts.len >= 2) {
         plot_open_joined(ist, ipts.head(0), ipts.head(1), ipts.tail(2), ipts.tail(1));
       }
@@ -259,8 +266,8 @@ struct StrokeWalker {
       if (pt_eq(target, current)) return;
       const Pt first_dash_point = current;
       Slope slope{target.x - first_dash_point.x, target.y - first_dash_point.y};
-      cur_slope = slope;
-      slope_normalize(cur_slope);
+      cur_raw = slope;
+      cur_set = true;
       xf_dist(c.inv, slope.dx, slope.dy);
       const double total_len = slope_normalize(slope);
       double remaining = total_len;
@@ -350,7 +357,7 @@ struct StrokeWalker {
           st.clockwise = -1;
         } else {
           if (pts.len == 1) {
-            plot_dotted_dashed(st, pts.first(), cur_slope);
+            plot_dotted_dashed(st, pts.first(), unit_slope(cur_raw, cur_set));
           } else if (pts.len == 2) {
             plot_single(st, pts.head(0), pts.head(1));
           } else {
@@ -394,10 +401,18 @@ Z2D_D int pen_run_len(int idx, int end, int npen, bool cw) {
 Z2D_D void unit_plan(const StrokeCtx& c, uint32_t kind, const double* __restrict__ q, UnitPlan& P) {
   const uint32_t k = kind & kUnitKindMask;
   const bool flag_cw = (kind & kUnitCw) != 0;
-  if (k == kUnitJoin) {
-    const Pt p0{q[0], q[1]}, p1{q[2], q[3]}, p2{q[4], q[5]};
+  const bool is_join = k == kUnitJoin, is_cap = k == kUnitCap;
+  // Joins and caps sit next to each other in the unit array (a dash = cap, cap or join, cap, cap): the face of the first
+  // segment and the pen search are done at ONE place for both kinds so that the lanes of a warp run them together.
+  const Pt p0{q[0], q[1]}, p1{q[2], q[3]}, p2{q[4], q[5]};
+  Face fa{}, fb{};
+  if (is_join || is_cap) fa = face_init(p0, p1, c);
+  if (is_join) fb = face_init(p1, p2, c);
+  bool need_run = false, run_cw = true;
+  Slope from{0, 0}, to{0, 0};
+  if (is_join) {
+    const Face &in = fa, &out = fb;
     const uint32_t join_mode = kind >> kUnitJoinShift;
-    const Face in = face_init(p0, p1, c), out = face_init(p1, p2, c);
     const int cmp = slope_compare(in.dev, out.dev);
     const bool join_cw = cmp < 0;
     P.swap = join_cw != flag_cw;
@@ -408,11 +423,10 @@ Z2D_D void unit_plan(const StrokeCtx& c, uint32_t kind, const double* __restrict
       P.n_in = 1;
     } else if (join_mode == Z2D_JOIN_ROUND) {
       P.h[0] = join_cw ? in.p1_ccw : in.p1_cw;
-      int idx, end;
-      pen_range(c, in.dev, out.dev, join_cw, idx, end);
-      P.run_start = idx;
-      P.run_len = pen_run_len(idx, end, c.npen, join_cw);
-      P.run_cw = join_cw;
+      need_run = true;
+      from = in.dev;
+      to = out.dev;
+      run_cw = join_cw;
       P.centre = p1;
       P.t = join_cw ? out.p0_ccw : out.p0_cw;
       P.n_tail = 1;
@@ -426,8 +440,8 @@ Z2D_D void unit_plan(const StrokeCtx& c, uint32_t kind, const double* __restrict
     P.in[0] = join_cw ? in.p1_cw : in.p1_ccw;
     P.in[1] = p1;
     P.in[2] = join_cw ? out.p0_cw : out.p0_ccw;
-  } else if (k == kUnitCap) {
-    const Face f = face_init(Pt{q[0], q[1]}, Pt{q[2], q[3]}, c);
+  } else if (is_cap) {
+    const Face& f = fa;
     const bool clockwise = flag_cw;
     if (c.cap == Z2D_CAP_BUTT) {
       P.n_head = 2;
@@ -446,21 +460,19 @@ Z2D_D void unit_plan(const StrokeCtx& c, uint32_t kind, const double* __restrict
       P.h[0] = clockwise ? f.p1_ccw : f.p1_cw;
       P.t = clockwise ? f.p1_cw : f.p1_ccw;
       P.n_tail = 1;
-      int idx, end;
-      pen_range(c, f.dev, Slope{-f.dev.dx, -f.dev.dy}, clockwise, idx, end);
-      P.run_start = idx;
-      P.run_len = pen_run_len(idx, end, c.npen, clockwise);
-      P.run_cw = clockwise;
+      need_run = true;
+      from = f.dev;
+      to = Slope{-f.dev.dx, -f.dev.dy};
+      run_cw = clockwise;
       P.centre = f.p1;
     }
   } else if (k == kUnitDotRound) {
-    P.centre = Pt{q[0], q[1]};
+    P.centre = p0;
     P.run_start = 0;
     P.run_len = c.npen;
     P.run_cw = true;
   } else if (k == kUnitDotSquare) {
-    const Pt point{q[0], q[1]};
-    const Face f = face_make(point, point, Slope{q[2], q[3]}, c);
+    const Face f = face_make(p0, p0, Slope{q[2], q[3]}, c);
     double ox = f.user.dx * f.half_width, oy = f.user.dy * f.half_width;
     xf_dist(c.ctm, ox, oy);
     P.n_head = 4;
@@ -468,6 +480,13 @@ Z2D_D void unit_plan(const StrokeCtx& c, uint32_t kind, const double* __restrict
     P.h[1] = {f.p1_cw.x + ox, f.p1_cw.y + oy};
     P.h[2] = {f.p1_ccw.x + ox, f.p1_ccw.y + oy};
     P.h[3] = {f.p1_ccw.x - ox, f.p1_ccw.y - oy};
+  }
+  if (need_run) {
+    int idx, end;
+    pen_range(c, from, to, run_cw, idx, end);
+    P.run_start = idx;
+    P.run_len = pen_run_len(idx, end, c.npen, run_cw);
+    P.run_cw = run_cw;
   }
 }
 
@@ -642,15 +661,13 @@ struct PoolSink {  // Polygon.addEdge into pool slots; horizontal edges leave a 
   Z2D_D void add(Pt p0, Pt p1) {
     const double ax = p0.x, ay = p0.y, bx = p1.x, by = p1.y;
     const uint32_t at = pos++;
-    DevEdge e;
-    if (ay < by) {
-      e = {ay, by, ax, (bx - ax) / (by - ay)};
-    } else if (ay > by) {
-      e = {ay, by, bx, (ax - bx) / (ay - by)};
-    } else {
+    if (ay == by) {
       if (at < cap) edge_draw[at] = kNoUnit;
       return;
     }
+    // Polygon.addEdge: {y0, y1, x of the upper end, dx/dy}.  (bx - ax) / (by - ay) and (ax - bx) / (ay - by) are the same
+    // double (both operands negated exactly), so one division serves both directions.
+    const DevEdge e{ay, by, ay < by ? ax : bx, (bx - ax) / (by - ay)};
     if (at < cap) {
       edges[at] = e;
       edge_draw[at] = draw;
@@ -666,11 +683,14 @@ struct PoolSink {  // Polygon.addEdge into pool slots; horizontal edges leave a 
   Z2D_D void commit(DevDraw* __restrict__ draws) const {
     if (!n_live) return;
     DevDraw& d = draws[draw];
-    atomicMin(&d.ext[0], f64_order(top));
-    atomicMax(&d.ext[1], f64_order(bottom));
-    atomicMin(&d.ext[2], f64_order(left));
-    atomicMax(&d.ext[3], f64_order(right));
-    atomicAdd(&d.n_edges, n_live);
+    // most units lie inside what earlier units of the draw already reported: look before paying for an atomic
+    const volatile long long* ext = d.ext;
+    const long long t = f64_order(top), b = f64_order(bottom), l = f64_order(left), r = f64_order(right);
+    if (t < ext[0]) atomicMin(&d.ext[0], t);
+    if (b > ext[1]) atomicMax(&d.ext[1], b);
+    if (l < ext[2]) atomicMin(&d.ext[2], l);
+    if (r > ext[3]) atomicMax(&d.ext[3], r);
+    if (*(const volatile uint32_t*)&d.n_edges == 0u) atomicAdd(&d.n_edges, n_live);  // only "any edge at all" is read back
   }
 };
 
