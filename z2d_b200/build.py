@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libz2d_cuda.so")
-SOURCES = ["kernels.cu", "z2d_lib.cu"]
-HEADERS = ["kernels.cuh", "z2d_batch.cuh", "z2d_device.cuh", "raster.cuh", "pattern.cuh", "composite.cuh", "stroke.cuh", "slowpath.cuh", "blue_noise_table.h",
+SOURCES = ["kernels.cu", "raster.cu", "z2d_lib.cu"]
+HEADERS = ["kernels.cuh", "z2d_batch.cuh", "z2d_device.cuh", "raster.cuh", "pattern.cuh", "composite.cuh", "stroke.cuh", "stroke_units.cuh", "geom.cuh", "smallbatch.cuh", "slowpath.cuh", "blue_noise_table.h",
            "../../include/z2d_cuda.h"]
 # -fmad=false: the reference never fuses a*b+c and its results (f64 edge crossings,
 # f32 blend arithmetic) are reproduced bit-exactly only without contraction.

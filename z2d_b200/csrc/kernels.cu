@@ -780,7 +780,7 @@ template __global__ void k_band_lists<true>(const DevSurface*, uint32_t, const u
 
 }  // namespace z2d
 #include "pattern.cuh"
-#include "raster.cuh"
+#include "raster.cuh"  // blend helpers only: the K4 kernels are compiled in their own translation unit (raster.cu)
 namespace z2d {
 
 // =====================================================================================
@@ -986,7 +986,7 @@ void launch_stroke_units(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
                          DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap, cudaStream_t st) {
   if (!n_sp) return;
   cudaMemsetAsync(ctr, 0, 16, st);
-  k_stroke_walk<<<blocks_for(n_sp, 64), 64, 0, st>>>(sps, n_sp, nodes, draws, (const PenV*)pens, dashes, order, (StrokeUnit*)units, unit_cap,
+  k_stroke_walk<<<blocks_for((size_t)n_sp * Z2D_WALK_SPREAD, Z2D_WALK_THREADS), Z2D_WALK_THREADS, 0, st>>>(sps, n_sp, nodes, draws, (const PenV*)pens, dashes, order, (StrokeUnit*)units, unit_cap,
                                                      (StrokeLink*)links, link_cap, ctr);
   if (unit_cap)
     k_stroke_units<<<blocks_for(unit_cap, 128), 128, 0, st>>>((const StrokeUnit*)units, unit_cap, ctr, draws, (const PenV*)pens, dashes, (Pt*)ports,
@@ -1064,11 +1064,6 @@ void launch_expand_glyphs(const GlyphInst* inst, uint32_t n, const z2d_node* cac
   if (n) k_expand_glyphs<<<n, 128, 0, st>>>(inst, cache, nodes);
 }
 void launch_small_batch(const SmallArgs& A, cudaStream_t st) { k_small_batch<<<1, kSmallThreads, 0, st>>>(A); }
-void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st) {
-  if (!A.n_tiles) return;
-  if (rich) k_raster_tiles_rich<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
-  else k_raster_tiles<<<blocks_for(A.n_tiles, kRasterThreads / 32), kRasterThreads, 0, st>>>(A);
-}
 void launch_composite(const CompArgs& A, int sm_count, cudaStream_t st) {
   const size_t n = (size_t)A.scan_w * (size_t)A.rows;
   if (n == 0) return;

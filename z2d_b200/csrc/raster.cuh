@@ -19,7 +19,7 @@ namespace z2d {
 Z2D_D RGBA16 mask_mul16(RGBA16 s, int m) { return {iM(s.r, m), iM(s.g, m), iM(s.b, m), iM(s.a, m)}; }  // dst_in(dst:=s, src:=alpha8 m)
 
 // generic StrideCompositor batch: [dst_in(pattern, mask)]? ; op   (shared.zig:24-45, 78-102), any source / precision
-__device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables T, uint32_t precision, uint32_t fmt, uint32_t raw,
+static __device__ __noinline__ uint32_t composite_generic(const DevDraw& d, const GradTables T, uint32_t precision, uint32_t fmt, uint32_t raw,
                                                    int mask8, bool use_mask, int x, int y) {
   if (precision == Z2D_PRECISION_INTEGER) {
     RGBA16 s = src_int(d.src, T, x, y, 0);
@@ -259,7 +259,7 @@ Z2D_D void cross_pass(const DevEdge* __restrict__ be, const int4* __restrict__ h
 }
 
 // rare: more than 60 edges of one draw cross one tile; 32 planes in local memory, one row at a time
-__device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be,
+static __device__ __noinline__ uint64_t cross_row_wide(const DevEdge* __restrict__ be, const int4* __restrict__ hd, uint32_t n_be,
                                                 const uint16_t* __restrict__ clist, uint32_t ncross, int ys, int sx0, int ncols, bool even_odd,
                                                 int wl) {
   uint64_t p[32];
@@ -669,7 +669,7 @@ Z2D_D uint32_t nonzero_bytes(uint32_t x) { return (uint32_t)__popc(((x & 0x7f7f7
 // path.  Stages the gradient, its stops and the source record in shared memory once per pair and samples with the row-invariant
 // part of the offset arithmetic hoisted (a lane's 8 pixels share a row).  Returns the number of pixels composited by this lane.
 // flags: 1 unbounded MSAA pre-clear, 2 every pixel of the region is composited (supersample), 4 the lane's row is on the surface.
-__device__ __noinline__ uint32_t pattern_tile(const DevDraw* dp, const DrawHot* hp, GradTables T, uint32_t* px, DevGrad* sg, float* soff,
+static __device__ __noinline__ uint32_t pattern_tile(const DevDraw* dp, const DrawHot* hp, GradTables T, uint32_t* px, DevGrad* sg, float* soff,
                                               float4* scol, DevSrc* psrc, uint32_t cov_e, uint32_t cov_o, int px0, int py, int sfc_w,
                                               uint32_t fmt, uint32_t flags) {
   const int lane = (int)(threadIdx.x & 31u);
@@ -975,9 +975,11 @@ Z2D_D void raster_tiles_body(const RasterArgs& A) {
   }
 }
 
+#ifdef Z2D_RASTER_TU  // the kernels are instantiated by raster.cu only; kernels.cu includes this file for the blend helpers
 __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_MIN_CTAS) k_raster_tiles(const __grid_constant__ RasterArgs A) { raster_tiles_body<false>(A); }
 __global__ void __launch_bounds__(kRasterThreads, Z2D_RASTER_RICH_MIN_CTAS) k_raster_tiles_rich(const __grid_constant__ RasterArgs A) {
   raster_tiles_body<true>(A);
 }
+#endif
 
 }  // namespace z2d
