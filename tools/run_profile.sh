@@ -15,7 +15,8 @@ cap '^k_raster_tiles$' raster 2 $B
 cap 'k_flatten_nodes' flatten 9 $B
 cap 'k_composite_fast' composite 1 $B
 cap 'k_raster_tiles_rich' raster_strokes 2 $B --workload c3
-cap 'k_flatten_count' flatten_strokes 2 $B --workload c3
+cap 'k_stroke_walk' stroke_walk 2 $B --workload c3
+cap 'k_stroke_units' stroke_units 2 $B --workload c3
 cap 'k_composite_gen' composite_gen 2 python tools/c4_one.py rgba linear none src_over integer
 cap 'k_composite_lut' composite_lut 2 python tools/c4_one.py alpha8 pixel none src_over integer
 ls -la gpurun_out/ | tail -30

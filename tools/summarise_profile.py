@@ -45,7 +45,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "smsp__sass_inst_executed_op_local_ld.sum",
         "smsp__sass_inst_executed_op_local_st.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed"]
-for kern in ("raster", "flatten", "composite", "raster_strokes", "flatten_strokes", "composite_gen", "composite_lut"):
+for kern in ("raster", "flatten", "composite", "raster_strokes", "flatten_strokes", "stroke_walk", "stroke_units", "composite_gen", "composite_lut"):
     try:
         rows = list(csv.reader(open(G + f"{kern}_raw.csv")))
     except FileNotFoundError:

@@ -878,9 +878,10 @@ int run_isolated(z2d_ctx* c, Batch& B) {
   launches = 2;
   CK(c, cudaGetLastError());
   for (int i = 1; i <= 4; i++) CK(c, cudaEventRecord(c->ev[i], st));
-  // the pinned batch arrays are reused by the next draw: their async uploads must have landed (the tile
-  // pipeline gets this from its read-backs)
-  CK(c, cudaStreamSynchronize(st));
+  // the pinned batch arrays are reused by the next draw: their async uploads must have landed (the tile pipeline gets this
+  // from its read-backs).  Only the copies are waited for -- the hairline kernel itself stays asynchronous, so a hairline in
+  // the middle of a scene no longer drains the device.
+  CK(c, cudaEventSynchronize(c->ev_up));
   z2d_stats& s = c->stats;
   memset(&s, 0, sizeof s);
   s.draws = 1;
