@@ -1032,12 +1032,15 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
 }
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
                        uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint4* items, const uint32_t* band_off,
-                       const uint2* band_xr, cudaStream_t st) {
+                       const uint2* band_xr, uint32_t max_tiles_y, cudaStream_t st) {
   if (!n_chunks) return;
+  // a thread per tile row (a 4096-row canvas has 256): each walks the chunk's 256 boxes serially, and in the write pass follows
+  // every hit with two dependent loads, so the rows must not share threads (64 threads: 168 us on config 3; 256: see profiles)
+  const unsigned threads = max_tiles_y > 128 ? 256u : (max_tiles_y > 64 ? 128u : 64u);
   if (write)
-    k_band_lists<true><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
+    k_band_lists<true><<<n_chunks, threads, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
   else
-    k_band_lists<false><<<n_chunks, 64, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
+    k_band_lists<false><<<n_chunks, threads, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
 }
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {

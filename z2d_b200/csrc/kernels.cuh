@@ -79,7 +79,7 @@ void launch_bin_scatter(const DevEdge* edges, const uint32_t* edge_draw, uint32_
 // chunk_base[s] = number of (surface, kDrawChunk-draw chunk) blocks before surface s; one block per chunk
 void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const uint32_t* work_base, const uint32_t* chunk_base,
                        uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint4* items, const uint32_t* band_off,
-                       const uint2* band_xr, cudaStream_t st);
+                       const uint2* band_xr, uint32_t max_tiles_y, cudaStream_t st);
 // exact scanline replay of the draws k_setup_draws gave row records (counters[4] rows, counters[5] scratch slots)
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st);

@@ -114,7 +114,7 @@ struct z2d_sfc {
 
 struct BatchMeta {  // shape of the most recently uploaded batch (kept for z2d_replay)
   bool valid = false;
-  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0, n_srcs = 0, n_unit_sp = 0;
+  uint32_t n_draws = 0, n_sp = 0, n_sfc = 0, n_tiles = 0, n_work = 0, n_par_sp = 0, n_chunks = 0, n_strokes = 0, n_srcs = 0, n_unit_sp = 0, max_tiles_y = 0;
   int set = 0;  // which InputSet holds the batch
   size_t n_nodes = 0, h2d_bytes = 0;
 };
@@ -634,7 +634,7 @@ restart:
   CK(c, scan(c->d_draw_bands, c->d_draw_band_off, n_draws));
   CK(c, c->d_list_cnt.ensure((size_t)n_work * 4 + 16));
   launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
-                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, st);
+                    c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, m.max_tiles_y, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
   CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + n_cnt, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
@@ -719,7 +719,7 @@ restart:
   // K3b (write half): ordered draw list per surface tile-row
   launch_band_lists(true, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
                     c->d_boxes.as<DrawBox>(), nullptr, c->d_list_off.as<uint32_t>(), c->d_list_items.as<uint4>(), c->d_band_off.as<uint32_t>(),
-                    c->d_band_xr.as<uint2>(), st);
+                    c->d_band_xr.as<uint2>(), m.max_tiles_y, st);
   CK(c, cudaEventRecord(c->ev[3], st));
 
   nvtxRangePop();
@@ -1024,6 +1024,8 @@ int flush_impl(z2d_ctx* c, Batch& B) {
   m.n_srcs = (uint32_t)B.srcs.size();
   m.n_sfc = n_sfc;
   m.n_tiles = n_tiles;
+  m.max_tiles_y = 0;
+  for (const DevSurface& d : sfcs) m.max_tiles_y = std::max(m.max_tiles_y, (uint32_t)d.tiles_y);
   m.n_work = n_work;
   m.n_chunks = chunk_base[n_sfc];
   m.n_nodes = B.nodes.n;
