@@ -165,3 +165,19 @@ def test_surface_composite_at_negative_and_positive_offsets_matches_oracle(cuda,
             if dst_fmt == Format.rgb:
                 res = [r.reshape(-1, 4)[:, :3] for r in res]
             assert np.array_equal(res[0], res[1]), f"{dst_fmt.name} <- {src_fmt.name} at ({dx},{dy}) {op.name}"
+
+
+def test_stroke_pool_and_counted_edges_share_the_edge_array():
+    """The unit stroker writes stroke edges into a pool at the front of the edge array before the counted total of the batch is
+    known (z2d_lib.cu run_pipeline).  On a FRESH context: a small stroke batch sizes the pool; a batch with a few strokes and
+    thousands of fills then needs a larger array after the pool was written (it must survive the reallocation); a batch with
+    many more strokes than the capacities allow is redone with larger ones.  Every call is compared with the oracle."""
+    from tests.fuzz_util import assert_scene_matches
+    from z2d_b200.cuda_backend import CudaBackend
+    cb = CudaBackend()
+    cb.set_chunk(0)  # one batch per scene
+    size = 512
+    assert_scene_matches(cb, workloads.mixed_scene(0, size, n_fills=4, n_strokes=40, n_gradients=0), max_undefined=3)
+    assert_scene_matches(cb, workloads.mixed_scene(1, size, n_fills=3000, n_strokes=30, n_gradients=0), max_undefined=3)
+    assert_scene_matches(cb, workloads.mixed_scene(2, size, n_fills=4, n_strokes=900, n_gradients=0), max_undefined=3)
+    assert_scene_matches(cb, workloads.mixed_scene(3, size, n_fills=200, n_strokes=200, n_gradients=4), max_undefined=3)

@@ -254,19 +254,9 @@ __global__ void k_mark_nodes(const DevSubPath* __restrict__ sps, uint32_t n_sp, 
   for (uint32_t k = sp.node_begin; k < sp.node_end; k++) node_sp[k] = i;
 }
 
-// One node of a node-parallel sub-path (line_to / curve_to / close_path): count (EMIT = false: also extents) or emit its edges.
-template <bool EMIT>
-Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws,
-                        uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges,
-                        uint32_t* __restrict__ edge_draw) {
-  DevDraw& d = draws[sp.draw];
-  EdgeSink<EMIT> sink;
-  sink.scale = d.scale;
-  if (EMIT) {
-    sink.out = edges + offs[i];
-    sink.out_draw = edge_draw + offs[i];
-    sink.draw = sp.draw;
-  }
+// The edges of one node of a node-parallel sub-path (line_to / curve_to / close_path) into `sink`.
+template <class Sink>
+Z2D_D void flatten_node_into(uint32_t i, const DevSubPath& sp, const z2d_node& nd, const z2d_node* __restrict__ nodes, double tolerance, Sink& sink) {
   const z2d_node pv = nodes[i - 1];  // move_to, line_to or curve_to
   Pt last = pv.tag == Z2D_NODE_CURVE_TO ? Pt{pv.p[4], pv.p[5]} : Pt{pv.p[0], pv.p[1]};
   auto line_to = [&](Pt p) Z2D_LAMBDA {
@@ -284,7 +274,7 @@ Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, co
     if (pt_eq(a, b) && pt_eq(c, e)) {  // Spline.zig:39-42
       line_to(e);
     } else {
-      const double tol_sq = d.tolerance * d.tolerance;
+      const double tol_sq = tolerance * tolerance;
       Knots stack[kSplineStack];
       int sp_n = 0;
       Knots k{a, b, c, e};
@@ -303,6 +293,22 @@ Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, co
     const z2d_node mv = nodes[sp.node_begin];
     line_to({mv.p[0], mv.p[1]});
   }
+}
+
+// One node: count (EMIT = false: also extents) or emit its edges at the offset the scan of the counts gave it.
+template <bool EMIT>
+Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws,
+                        uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, DevEdge* __restrict__ edges,
+                        uint32_t* __restrict__ edge_draw) {
+  DevDraw& d = draws[sp.draw];
+  EdgeSink<EMIT> sink;
+  sink.scale = d.scale;
+  if (EMIT) {
+    sink.out = edges + offs[i];
+    sink.out_draw = edge_draw + offs[i];
+    sink.draw = sp.draw;
+  }
+  flatten_node_into(i, sp, nd, nodes, d.tolerance, sink);
   if (!EMIT) {
     counts[i] = sink.n;
     if (sink.n > 0) {
@@ -345,6 +351,81 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
     return;
   }
   flatten_node<EMIT>(i, sp, nd, nodes, draws, counts, offs, edges, edge_draw);
+}
+
+// ---- node-parallel flattening in ONE pass.  The count pass above runs the whole subdivision just to learn how many edges
+// a curve yields (0.4 of config 2's 1.2 ms of flattening).  An upper bound is free: with M = max |second difference| of the
+// control polygon, the reference's flatness measure (Knots.errorSq: distance of the inner control points from the chord)
+// is <= M, and de Casteljau halving divides the second differences by 4 (a - 2ab + abbc = (a - 2b + c) / 4,
+// ab - 2abbc + fin = (a - b - c + d) / 8), so no piece is split beyond depth k = min{k : M^2 / 16^k < tol^2} and a curve
+// yields at most 2^k edges.  Nodes take ranges of that size from the edge pool (scan + one atomicAdd per batch), write their
+// edges, and leave the rest of the range dead (edge_draw = ~0, skipped by binning).  Extents come from the same pass, so K2
+// runs after it.  A node that would exceed its bound (NaN / infinite coordinates) raises ctr[4] and the batch is redone by
+// the two-pass kernels.
+Z2D_D uint32_t curve_edge_bound(Pt a, Pt b, Pt c, Pt e, double tol) {
+  if (pt_eq(a, b) && pt_eq(c, e)) return 1u;  // Spline.zig:39-42
+  const double d0x = a.x - 2.0 * b.x + c.x, d0y = a.y - 2.0 * b.y + c.y;
+  const double d1x = b.x - 2.0 * c.x + e.x, d1y = b.y - 2.0 * c.y + e.y;
+  const double m0 = d0x * d0x + d0y * d0y, m1 = d1x * d1x + d1y * d1y;
+  double ratio = (m0 > m1 ? m0 : m1) / (tol * tol) * 1.01;  // (1 % for the rounding of the halving arithmetic)
+  uint32_t k = 0;
+  while (ratio >= 1.0 && k < 20u) {
+    ratio *= 0.0625;
+    k++;
+  }
+  return 1u << k;
+}
+
+__global__ void k_node_bounds(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
+                              const z2d_node* __restrict__ nodes, const DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
+                              uint32_t* __restrict__ curve_list, uint32_t* __restrict__ n_curves) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const uint32_t spi = node_sp[i];
+  uint32_t n = 0;
+  if (spi != 0xffffffffu) {
+    const z2d_node nd = nodes[i];
+    if (nd.tag == Z2D_NODE_CURVE_TO) {
+      const z2d_node pv = nodes[i - 1];
+      const Pt a = pv.tag == Z2D_NODE_CURVE_TO ? Pt{pv.p[4], pv.p[5]} : Pt{pv.p[0], pv.p[1]};
+      n = curve_edge_bound(a, {nd.p[0], nd.p[1]}, {nd.p[2], nd.p[3]}, {nd.p[4], nd.p[5]}, draws[sps[spi].draw].tolerance);
+      curve_list[atomicAdd(n_curves, 1u)] = i;
+    } else if (nd.tag != Z2D_NODE_MOVE_TO) {
+      n = 1;
+    }
+  }
+  counts[i] = n;
+}
+
+// ctr[3] = first pool slot of the batch's node ranges (ctr[2] is the pool cursor the stroke kernels share)
+__global__ void k_take_node_range(uint32_t* __restrict__ ctr, const uint32_t* __restrict__ node_offs, uint32_t n_nodes) {
+  ctr[3] = atomicAdd(&ctr[2], node_offs[n_nodes] - node_offs[0]);
+}
+
+template <bool CURVES>
+__global__ void k_flatten_nodes_pool(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
+                                     const z2d_node* __restrict__ nodes, DevDraw* __restrict__ draws, const uint32_t* __restrict__ node_offs,
+                                     uint32_t* __restrict__ ctr, DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw, uint32_t edge_cap,
+                                     const uint32_t* __restrict__ curve_list, const uint32_t* __restrict__ n_curves) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (CURVES) {
+    if (i >= *n_curves) return;
+    i = curve_list[i];
+  } else if (i >= n_nodes) {
+    return;
+  }
+  const uint32_t spi = node_sp[i];
+  if (spi == 0xffffffffu) return;
+  const z2d_node nd = nodes[i];
+  if (nd.tag == Z2D_NODE_MOVE_TO || (!CURVES && nd.tag == Z2D_NODE_CURVE_TO)) return;
+  const DevSubPath sp = sps[spi];
+  const uint32_t first = ctr[3] + (node_offs[i] - node_offs[0]), bound = node_offs[i + 1] - node_offs[i];
+  const uint32_t end = first + bound;
+  PoolSink sink{edges, edge_draw, sp.draw, first, end < edge_cap ? end : edge_cap};
+  sink.scale = draws[sp.draw].scale;
+  flatten_node_into(i, sp, nd, nodes, draws[sp.draw].tolerance, sink);
+  if (sink.pos > end) ctr[4] = 1u;  // more edges than the bound allows: the batch is redone by the two-pass kernels
+  sink.commit(draws);
 }
 
 // =====================================================================================
@@ -985,7 +1066,6 @@ void launch_stroke_units(const DevSubPath* sps, uint32_t n_sp, const z2d_node* n
                          const uint32_t* order, void* units, uint32_t unit_cap, void* links, uint32_t link_cap, void* ports, uint32_t* ctr,
                          DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap, cudaStream_t st) {
   if (!n_sp) return;
-  cudaMemsetAsync(ctr, 0, 16, st);
   k_stroke_walk<<<blocks_for((size_t)n_sp * Z2D_WALK_SPREAD, Z2D_WALK_THREADS), Z2D_WALK_THREADS, 0, st>>>(sps, n_sp, nodes, draws, (const PenV*)pens, dashes, order, (StrokeUnit*)units, unit_cap,
                                                      (StrokeLink*)links, link_cap, ctr);
   if (unit_cap)
@@ -1012,6 +1092,26 @@ void launch_flatten_nodes(bool emit, const DevSubPath* sps, uint32_t n_sp, uint3
     k_flatten_nodes<true, false><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw, curve_list, n_curves);
     k_flatten_nodes<true, true><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, nullptr, offs, edges, edge_draw, curve_list, n_curves);
   }
+}
+// single-pass node-parallel flattening: bounds (first call, before the scan of `counts`), then edges into the pool
+void launch_node_bounds(const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes, const DevDraw* draws,
+                        uint32_t* counts, uint32_t* curve_list, cudaStream_t st) {
+  if (!n_nodes || !n_sp) return;
+  uint32_t* n_curves = curve_list + n_nodes;
+  cudaMemsetAsync(node_sp, 0xff, (size_t)n_nodes * 4, st);
+  cudaMemsetAsync(n_curves, 0, 4, st);
+  k_mark_nodes<<<blocks_for(n_sp, 128), 128, 0, st>>>(sps, n_sp, node_sp);
+  k_node_bounds<<<blocks_for(n_nodes, 128), 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, counts, curve_list, n_curves);
+}
+void launch_flatten_nodes_pool(const DevSubPath* sps, const uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes, DevDraw* draws,
+                               const uint32_t* node_offs, uint32_t* ctr, DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap,
+                               const uint32_t* curve_list, cudaStream_t st) {
+  if (!n_nodes) return;
+  const uint32_t* n_curves = curve_list + n_nodes;
+  const uint32_t nb = blocks_for(n_nodes, 128);
+  k_take_node_range<<<1, 1, 0, st>>>(ctr, node_offs, n_nodes);
+  k_flatten_nodes_pool<false><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, node_offs, ctr, edges, edge_draw, edge_cap, curve_list, n_curves);
+  k_flatten_nodes_pool<true><<<nb, 128, 0, st>>>(sps, node_sp, n_nodes, nodes, draws, node_offs, ctr, edges, edge_draw, edge_cap, curve_list, n_curves);
 }
 void launch_setup_draws(DevDraw* draws, uint32_t n, const DevSurface* sfcs, uint32_t* draw_bands, DrawBox* boxes, unsigned long long* counters, cudaStream_t st) {
   if (n) k_setup_draws<<<blocks_for(n, 128), 128, 0, st>>>(draws, n, sfcs, draw_bands, boxes, counters);

@@ -59,6 +59,13 @@ void launch_flatten_count(const DevSubPath* sps, uint32_t n_sp, const z2d_node* 
 void launch_sp_order(const DevSubPath* sps, uint32_t n_sp, const DevDraw* draws, uint32_t* keys_scratch, uint32_t* order, cudaStream_t st);
 void launch_flatten_emit(const DevSubPath* sps, uint32_t n_sp, const z2d_node* nodes, const DevDraw* draws, const uint32_t* sp_off,
                          DevEdge* edges, uint32_t* edge_draw, const void* pens, const double* dashes, const uint32_t* order, cudaStream_t st);
+// single-pass node-parallel flattening (kernels.cu, k_node_bounds / k_flatten_nodes_pool): per-node upper bounds into `counts`
+// (then scanned by the caller), edges into the pool at ctr[3] + offset; ctr[4] != 0: a node exceeded its bound
+void launch_node_bounds(const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes, const DevDraw* draws,
+                        uint32_t* counts, uint32_t* curve_list, cudaStream_t st);
+void launch_flatten_nodes_pool(const DevSubPath* sps, const uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes, DevDraw* draws,
+                               const uint32_t* node_offs, uint32_t* ctr, DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap,
+                               const uint32_t* curve_list, cudaStream_t st);
 // unit stroker (stroke_units.cuh) for the sub-paths flagged kSpStrokeUnits: walker -> units -> links.  ctr[0..2] = units, links and
 // edge slots taken (they run past the capacities when those are too small: the caller enlarges and repeats).
 constexpr size_t kStrokeUnitBytes = 64, kStrokeLinkBytes = 16, kStrokePortBytes = 64;  // per unit / link / unit

@@ -567,7 +567,8 @@ Z2D_D void unit_emit(const StrokeCtx& c, const UnitPlan& P, Pt* __restrict__ por
 constexpr uint32_t kUnitChunk = 8u, kLinkChunk = 16u;  // ids a walker thread takes from the global cursor at a time
 
 // ctr[0] units taken, ctr[1] links taken, ctr[2] edge slots taken (each may run past its capacity: nothing is written there
-// and the host redoes the batch with larger arrays)
+// and the host redoes the batch with larger arrays); ctr[3], ctr[4]: node ranges of the single-pass fill flattening (kernels.cu).
+// The caller zeroes ctr[0..8) before the first kernel of a batch.
 struct PoolRec {
   StrokeUnit* units;
   StrokeLink* links;
@@ -674,8 +675,9 @@ struct PoolSink {  // Polygon.addEdge into pool slots; horizontal edges leave a 
   uint32_t draw, pos, cap;
   uint32_t n_live = 0;
   double top = INFINITY, bottom = -INFINITY, left = INFINITY, right = -INFINITY;
+  double scale = 1.0;  // strokes plot pre-scaled contour points; fills scale here like Polygon.addEdge's caller
   Z2D_D void add(Pt p0, Pt p1) {
-    const double ax = p0.x, ay = p0.y, bx = p1.x, by = p1.y;
+    const double ax = p0.x * scale, ay = p0.y * scale, bx = p1.x * scale, by = p1.y * scale;
     const uint32_t at = pos++;
     if (ay == by) {
       if (at < cap) edge_draw[at] = kNoUnit;

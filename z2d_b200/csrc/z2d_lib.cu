@@ -216,6 +216,7 @@ struct z2d_ctx {
   uint32_t su_unit_cap = 0, su_link_cap = 0, su_edge_cap = 0;
   uint32_t last_scan_edges = 0;  // counted (non-pool) edges of the previous batch: sizes the edge array before the total is known
   bool stroke_units = true;      // Z2D_NO_STROKE_UNITS=1: every stroke through the sub-path stroker
+  bool fill_single_pass = true;  // Z2D_NO_FILL_SINGLE_PASS=1: node-parallel fills counted, scanned, then emitted (two passes)
   // glyph cache (z2d_glyph_cache_add): outlines in Path space, host mirror + device copy; per glyph its node range and sub-paths
   struct GlyphEntry {
     uint32_t node_off, n_nodes, sp_off, n_sp;
@@ -567,6 +568,7 @@ int run_pipeline(z2d_ctx* c, bool replay) {
   };
   NvtxRange r_batch("z2d batch");
   int su_tries = 0;
+  bool par_pool = m.n_par_sp != 0 && c->fill_single_pass;  // node-parallel fills flattened in one pass into the edge pool
 restart:
   nvtxRangePushA("z2d K0-K1 expand + flatten (count)");
   CK(c, c->d_counters.ensure(64));
@@ -594,27 +596,43 @@ restart:
   if (par) {
     CK(c, c->d_node_sp.ensure((size_t)n_nodes * 4 + 16));
     CK(c, c->d_curve_list.ensure(((size_t)n_nodes + 1) * 4 + 16));
-    launch_flatten_nodes(false, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
-                         c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr,
-                         c->d_curve_list.as<uint32_t>(), st);
+    if (par_pool)  // one pass: upper bounds now, edges (and extents) into the pool below
+      launch_node_bounds(S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
+                         c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, c->d_curve_list.as<uint32_t>(), st);
+    else
+      launch_flatten_nodes(false, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
+                           c->d_draws.as<DevDraw>(), c->d_sp_count.as<uint32_t>() + n_sp, nullptr, nullptr, nullptr,
+                           c->d_curve_list.as<uint32_t>(), st);
     launches += 5;
   }
   CK(c, scan(c->d_sp_count, c->d_sp_off, n_cnt));
   // K1 for ordinary strokes: the unit stroker writes its edges straight into the pool at the FRONT of the edge array, so the
   // array is sized before the counted total is known (the previous batch's, corrected after the read-back below)
   const bool units = m.n_unit_sp != 0;
+  const bool pool = units || par_pool;
+  if (pool) {
+    if (c->su_edge_cap == 0) c->su_edge_cap = 32u * n_nodes + 65536u;
+    CK(c, c->d_su_ctr.ensure(64));
+    CK(c, cudaMemsetAsync(c->d_su_ctr.p, 0, 32, st));
+    CK(c, c->d_edges.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * sizeof(DevEdge) + 32));
+    CK(c, c->d_edge_draw.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * 4 + 16));
+  }
+  if (par_pool) {
+    // (slots of a node's range beyond its last edge stay dead)
+    CK(c, cudaMemsetAsync(c->d_edge_draw.p, 0xff, (size_t)c->su_edge_cap * 4, st));
+    launch_flatten_nodes_pool(S.d_subpaths.as<DevSubPath>(), c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
+                              c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>() + n_sp, c->d_su_ctr.as<uint32_t>(), c->d_edges.as<DevEdge>(),
+                              c->d_edge_draw.as<uint32_t>(), c->su_edge_cap, c->d_curve_list.as<uint32_t>(), st);
+    launches += 3;
+  }
   if (units) {
     if (c->su_unit_cap == 0) {
       c->su_unit_cap = 4u * n_nodes + 4096u;
       c->su_link_cap = 2u * c->su_unit_cap;
-      c->su_edge_cap = 16u * c->su_unit_cap;
     }
     CK(c, c->d_su_units.ensure((size_t)c->su_unit_cap * kStrokeUnitBytes));
     CK(c, c->d_su_links.ensure((size_t)c->su_link_cap * kStrokeLinkBytes));
     CK(c, c->d_su_ports.ensure((size_t)c->su_unit_cap * kStrokePortBytes));
-    CK(c, c->d_su_ctr.ensure(64));
-    CK(c, c->d_edges.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * sizeof(DevEdge) + 32));
-    CK(c, c->d_edge_draw.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * 4 + 16));
     launch_stroke_units(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), S.pens, S.dashes, order,
                         c->d_su_units.p, c->su_unit_cap, c->d_su_links.p, c->su_link_cap, c->d_su_ports.p, c->d_su_ctr.as<uint32_t>(),
                         c->d_edges.as<DevEdge>(), c->d_edge_draw.as<uint32_t>(), c->su_edge_cap, st);
@@ -636,23 +654,33 @@ restart:
   launch_band_lists(false, S.sfcs, n_sfc, S.work_base, S.chunk_base, m.n_chunks,
                     c->d_boxes.as<DrawBox>(), c->d_list_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, m.max_tiles_y, st);
   CK(c, scan(c->d_list_cnt, c->d_list_off, n_work));
-  CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + n_cnt, 4, cudaMemcpyDeviceToHost, st));
+  // counted edges: sequential sub-paths (+ nodes, when they are not in the pool)
+  CK(c, cudaMemcpyAsync(c->h_total + 0, c->d_sp_off.as<uint32_t>() + (par_pool ? n_sp : n_cnt), 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 1, c->d_draw_band_off.as<uint32_t>() + n_draws, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 2, c->d_list_off.as<uint32_t>() + n_work, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(c->h_total + 4, c->d_counters.as<unsigned long long>() + 4, 16, cudaMemcpyDeviceToHost, st));  // k_edge_sim sizes
-  if (units) CK(c, cudaMemcpyAsync(c->h_total + 8, c->d_su_ctr.p, 12, cudaMemcpyDeviceToHost, st));
+  if (pool) CK(c, cudaMemcpyAsync(c->h_total + 8, c->d_su_ctr.p, 20, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
   uint32_t pool_edges = 0;
-  if (units) {
+  if (pool) {
     const uint32_t need_u = c->h_total[8], need_l = c->h_total[9], need_e = c->h_total[10];
-    if (need_u > c->su_unit_cap || need_l > c->su_link_cap || need_e > c->su_edge_cap) {
+    if (par_pool && (c->h_total[12] != 0u || need_e > (1u << 30))) {
+      // a node produced more edges than its bound (NaN / infinite coordinates), or the bounds add up to an absurd array
+      // (tolerance ~ 0): this batch goes through the two-pass kernels
+      par_pool = false;
+      nvtxRangePop();
+      goto restart;
+    }
+    if ((units && (need_u > c->su_unit_cap || need_l > c->su_link_cap)) || need_e > c->su_edge_cap) {
       // a capacity was too small (first batch with strokes, or denser strokes than before): enlarge and redo the batch from its
       // resident inputs.  When the unit array overflowed the edge need is only a lower bound, so this can take a second round.
       if (++su_tries > 4) return fail(c, "stroke unit capacities", cudaErrorUnknown);
       auto grow = [](uint32_t cap, uint32_t need) { return need > cap ? need + need / 8u + 1024u : cap; };
-      const bool units_lost = need_u > c->su_unit_cap;
-      c->su_unit_cap = grow(c->su_unit_cap, need_u);
-      c->su_link_cap = grow(c->su_link_cap, need_l);
+      const bool units_lost = units && need_u > c->su_unit_cap;
+      if (units) {
+        c->su_unit_cap = grow(c->su_unit_cap, need_u);
+        c->su_link_cap = grow(c->su_link_cap, need_l);
+      }
       c->su_edge_cap = grow(c->su_edge_cap, units_lost ? std::max(need_e, 12u * need_u) : need_e);
       nvtxRangePop();
       goto restart;
@@ -679,7 +707,7 @@ restart:
   CK(c, c->d_band_cursor.ensure((size_t)n_slots * 4 + 16));
   launch_flatten_emit(S.d_subpaths.as<DevSubPath>(), n_sp, S.d_nodes.as<z2d_node>(), c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>(),
                       scan_edges, scan_edge_draw, S.pens, S.dashes, order, st);
-  if (par) {
+  if (par && !par_pool) {
     launch_flatten_nodes(true, S.d_subpaths.as<DevSubPath>(), n_sp, c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
                          c->d_draws.as<DevDraw>(), nullptr, c->d_sp_off.as<uint32_t>() + n_sp, scan_edges,
                          scan_edge_draw, c->d_curve_list.as<uint32_t>(), st);
@@ -1301,6 +1329,7 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
   c->small_enabled = getenv("Z2D_NO_SMALL_BATCH") == nullptr;
   c->stroke_units = getenv("Z2D_NO_STROKE_UNITS") == nullptr;
+  c->fill_single_pass = getenv("Z2D_NO_FILL_SINGLE_PASS") == nullptr;
   if (cudaHostAlloc((void**)&c->h_total, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&c->h_small, 32, cudaHostAllocDefault) != cudaSuccess || c->d_blue.ensure(sizeof(z2d_blue_noise_64x64)) != cudaSuccess ||
       cudaMemcpyAsync(c->d_blue.p, z2d_blue_noise_64x64, sizeof(z2d_blue_noise_64x64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
     delete c;
