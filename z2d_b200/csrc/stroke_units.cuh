@@ -623,10 +623,11 @@ struct PoolRec {
     last_link = m.l;
   }
   Z2D_D void finish() {  // the ids of the last chunks that were never used
+    // (whole 16-byte headers: the consumers read them with one vector load)
     for (; u_next < u_end; u_next++)
-      if (u_next < unit_cap) units[u_next].kind = kUnitDead;
+      if (u_next < unit_cap) *reinterpret_cast<uint4*>(units + u_next) = make_uint4(kUnitDead, 0u, kNoUnit, 0u);
     for (; l_next < l_end; l_next++)
-      if (l_next < link_cap) links[l_next].from = kNoUnit;
+      if (l_next < link_cap) *reinterpret_cast<uint4*>(links + l_next) = make_uint4(kNoUnit, kNoUnit, 0u, kNoUnit);
   }
 };
 
