@@ -359,7 +359,7 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
 // is <= M, and de Casteljau halving divides the second differences by 4 (a - 2ab + abbc = (a - 2b + c) / 4,
 // ab - 2abbc + fin = (a - b - c + d) / 8), so no piece is split beyond depth k = min{k : M^2 / 16^k < tol^2} and a curve
 // yields at most 2^k edges.  Nodes take ranges of that size from the edge pool (scan + one atomicAdd per batch), write their
-// edges, and leave the rest of the range dead (edge_draw = ~0, skipped by binning).  Extents come from the same pass, so K2
+// edges, and mark the rest of the range dead (edge_draw = ~0, skipped by binning).  Extents come from the same pass, so K2
 // runs after it.  A node that would exceed its bound (NaN / infinite coordinates) raises ctr[4] and the batch is redone by
 // the two-pass kernels.
 Z2D_D uint32_t curve_edge_bound(Pt a, Pt b, Pt c, Pt e, double tol) {
@@ -425,6 +425,7 @@ __global__ void k_flatten_nodes_pool(const DevSubPath* __restrict__ sps, const u
   sink.scale = draws[sp.draw].scale;
   flatten_node_into(i, sp, nd, nodes, draws[sp.draw].tolerance, sink);
   if (sink.pos > end) ctr[4] = 1u;  // more edges than the bound allows: the batch is redone by the two-pass kernels
+  for (uint32_t p = sink.pos; p < sink.cap; p++) edge_draw[p] = 0xffffffffu;  // the rest of the range stays dead
   sink.commit(draws);
 }
 

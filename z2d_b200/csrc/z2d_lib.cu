@@ -618,8 +618,6 @@ restart:
     CK(c, c->d_edge_draw.ensure(((size_t)c->su_edge_cap + c->last_scan_edges) * 4 + 16));
   }
   if (par_pool) {
-    // (slots of a node's range beyond its last edge stay dead)
-    CK(c, cudaMemsetAsync(c->d_edge_draw.p, 0xff, (size_t)c->su_edge_cap * 4, st));
     launch_flatten_nodes_pool(S.d_subpaths.as<DevSubPath>(), c->d_node_sp.as<uint32_t>(), n_nodes, S.d_nodes.as<z2d_node>(),
                               c->d_draws.as<DevDraw>(), c->d_sp_off.as<uint32_t>() + n_sp, c->d_su_ctr.as<uint32_t>(), c->d_edges.as<DevEdge>(),
                               c->d_edge_draw.as<uint32_t>(), c->su_edge_cap, c->d_curve_list.as<uint32_t>(), st);
