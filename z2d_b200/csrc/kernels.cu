@@ -678,8 +678,10 @@ Z2D_D void bin_scatter_edge(uint32_t i, const DevEdge* __restrict__ edges, const
     if (slot >= band_cap) continue;  // (small-batch path: fixed capacity, the batch is redone by the sized pipeline)
     band_edges[slot] = e;
     band_hdr[slot] = h;
-    atomicMax(&band_xr[b].x, c_lo);
-    atomicMax(&band_xr[b].y, c_hi);
+    // (most edges of a row lie inside the column range the row's earlier edges reported: look before the atomic)
+    const volatile uint32_t* seen = reinterpret_cast<const volatile uint32_t*>(&band_xr[b]);
+    if (c_lo > seen[0]) atomicMax(&band_xr[b].x, c_lo);
+    if (c_hi > seen[1]) atomicMax(&band_xr[b].y, c_hi);
   }
 }
 __global__ void k_bin_scatter(const DevEdge* __restrict__ edges, const uint32_t* __restrict__ edge_draw, uint32_t n_edges,
