@@ -89,6 +89,17 @@ void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp
 #include "geom.cuh"
 namespace z2d {
 
+// Extents of a draw's edges, gathered from many threads: most of them lie inside what others already reported, so the
+// current value is looked at before paying for an atomic on a word that hundreds of threads share.
+Z2D_D void ext_commit(DevDraw& d, double top, double bottom, double left, double right) {
+  const volatile long long* ext = d.ext;
+  const long long t = f64_order(top), b = f64_order(bottom), l = f64_order(left), r = f64_order(right);
+  if (t < ext[0]) atomicMin(&d.ext[0], t);
+  if (b > ext[1]) atomicMax(&d.ext[1], b);
+  if (l < ext[2]) atomicMin(&d.ext[2], l);
+  if (r > ext[3]) atomicMax(&d.ext[3], r);
+}
+
 // fill_plotter.plot (tess/fill_plotter.zig:21-97) restricted to one sub-path
 // (the plotter state resets at every move_to).
 template <bool EMIT>
@@ -166,10 +177,7 @@ __global__ void __launch_bounds__(Z2D_FLATTEN_THREADS, Z2D_FLATTEN_MIN_CTAS) k_f
   sp_count[i] = sink.n;
   if (sink.unpaired && sink.n > 0) atomicOr(&d.flags, kDrawUnpaired);
   if (sink.n > 0) {
-    atomicMin(&d.ext[0], f64_order(sink.top));
-    atomicMax(&d.ext[1], f64_order(sink.bottom));
-    atomicMin(&d.ext[2], f64_order(sink.left));
-    atomicMax(&d.ext[3], f64_order(sink.right));
+    ext_commit(d, sink.top, sink.bottom, sink.left, sink.right);
     atomicAdd(&d.n_edges, sink.n);
   }
 }
@@ -312,10 +320,7 @@ Z2D_D void flatten_node(uint32_t i, const DevSubPath& sp, const z2d_node& nd, co
   if (!EMIT) {
     counts[i] = sink.n;
     if (sink.n > 0) {
-      atomicMin(&d.ext[0], f64_order(sink.top));
-      atomicMax(&d.ext[1], f64_order(sink.bottom));
-      atomicMin(&d.ext[2], f64_order(sink.left));
-      atomicMax(&d.ext[3], f64_order(sink.right));
+      ext_commit(d, sink.top, sink.bottom, sink.left, sink.right);
       atomicAdd(&d.n_edges, sink.n);
     }
   }

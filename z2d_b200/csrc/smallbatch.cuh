@@ -73,10 +73,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_batch(const __grid_c
     cnt_sp[i] = sink.n;
     if (sink.unpaired && sink.n > 0) atomicOr(&d.flags, kDrawUnpaired);
     if (sink.n > 0) {
-      atomicMin(&d.ext[0], f64_order(sink.top));
-      atomicMax(&d.ext[1], f64_order(sink.bottom));
-      atomicMin(&d.ext[2], f64_order(sink.left));
-      atomicMax(&d.ext[3], f64_order(sink.right));
+      ext_commit(d, sink.top, sink.bottom, sink.left, sink.right);
       atomicAdd(&d.n_edges, sink.n);
     }
   }

@@ -145,9 +145,15 @@ struct Batch {  // one recorded command batch (host side)
   std::vector<GlyphInst> ginst;  // glyph instances of the batch's text runs (z2d_fill_glyphs): expanded into `nodes` on the device
   std::vector<double> dashes;   // concatenated dash arrays of the batch's dashed strokes
   std::vector<double> pens;     // pen vertices, 6 doubles each {px,py,cw.dx,cw.dy,ccw.dx,ccw.dy}
-  double pen_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // parameters of the most recently built pen (thickness, tolerance, ctm)
-  uint32_t pen_last_begin = 0, pen_last_count = 0;
-  bool pen_cached = false;
+  // pens already built for this batch, by (thickness, tolerance, ctm): a scene strokes with a handful of widths, and a pen is
+  // up to ~60 sin / cos pairs on the host and 48 bytes per vertex over PCIe (config 3: 60 MB per 50 000 strokes before this)
+  struct PenEntry {
+    double key[8];
+    uint32_t begin, count;
+  };
+  static constexpr int kPenCache = 16;
+  PenEntry pen_cache[kPenCache];
+  int pen_cache_n = 0, pen_cache_next = 0;
 };
 
 struct InputSet {  // device copies of one batch's uploaded inputs; two sets, so that the upload of batch k+1 (copy stream)
@@ -447,10 +453,13 @@ double major_axis(const double* m, double radius) {
 // path uses) once per distinct (thickness, tolerance, CTM); the device only looks vertices up.
 void add_pen(z2d_ctx* c, DevDraw& d) {
   const double key[8] = {d.thickness, d.tolerance, d.ctm[0], d.ctm[1], d.ctm[2], d.ctm[3], d.ctm[4], d.ctm[5]};
-  if (c->rec->pen_cached && memcmp(key, c->rec->pen_key, sizeof key) == 0) {
-    d.pen_begin = c->rec->pen_last_begin;
-    d.pen_count = c->rec->pen_last_count;
-    return;
+  for (int k = 0; k < c->rec->pen_cache_n; k++) {
+    const Batch::PenEntry& e = c->rec->pen_cache[k];
+    if (memcmp(key, e.key, sizeof key) == 0) {
+      d.pen_begin = e.begin;
+      d.pen_count = e.count;
+      return;
+    }
   }
   const double radius = d.thickness / 2, tol = d.tolerance;
   int n;
@@ -490,10 +499,12 @@ void add_pen(z2d_ctx* c, DevDraw& d) {
   }
   d.pen_begin = (uint32_t)(base / 6);
   d.pen_count = (uint32_t)n;
-  memcpy(c->rec->pen_key, key, sizeof key);
-  c->rec->pen_last_begin = d.pen_begin;
-  c->rec->pen_last_count = d.pen_count;
-  c->rec->pen_cached = true;
+  Batch::PenEntry& e = c->rec->pen_cache[c->rec->pen_cache_next];  // round robin once the cache is full
+  memcpy(e.key, key, sizeof key);
+  e.begin = d.pen_begin;
+  e.count = d.pen_count;
+  c->rec->pen_cache_next = (c->rec->pen_cache_next + 1) % Batch::kPenCache;
+  if (c->rec->pen_cache_n < Batch::kPenCache) c->rec->pen_cache_n++;
 }
 
 cudaError_t upload(z2d_ctx* c, DevBuf& b, const void* src, size_t bytes) {
@@ -527,7 +538,8 @@ void clear_batch(z2d_ctx* c, Batch& B) {
   B.dashes.clear();
   B.ginst.clear();
   B.pens.clear();
-  B.pen_cached = false;
+  B.pen_cache_n = 0;
+  B.pen_cache_next = 0;
 }
 
 GradTables tables(z2d_ctx* c, const DevGrad* g, const float* so, const float4* sc) {
@@ -2067,7 +2079,11 @@ int32_t z2d_stroke(z2d_ctx* c, z2d_sfc* s, const z2d_pattern* pattern, const z2d
   int32_t rc = record_draw(c, s, pattern, nodes, n, d);
   if (rc != Z2D_OK && rc != Z2D_E_DEVICE) {
     c->rec->dashes.resize(std::min(save_d, c->rec->dashes.size()));
-    c->rec->pens.resize(std::min(save_p, c->rec->pens.size()));
+    if (c->rec->pens.size() > save_p) {  // the failed call built a pen: it goes, and with it the cache entry that names it
+      c->rec->pens.resize(save_p);
+      c->rec->pen_cache_n = 0;
+      c->rec->pen_cache_next = 0;
+    }
   }
   return rc;
 }
