@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_batch(const __grid_c
     int band;
     work_item(w, si, band);
     const DevSurface& s = A.sfcs[si];
-    A.list_cnt[w] = band_list_row<false>(band, s.draw_begin, s.draw_end, A.boxes, 0u, nullptr, nullptr, nullptr);
+    A.list_cnt[w] = band_list_row<false>(band, s.draw_begin, s.draw_end, reinterpret_cast<const int4*>(A.boxes), 0u, 0u, nullptr, nullptr, nullptr);
   }
   __syncthreads();
   const uint32_t n_items = block_scan_inplace(A.list_cnt, A.n_work, sh);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_batch(const __grid_c
     int band;
     work_item(w, si, band);
     const DevSurface& s = A.sfcs[si];
-    band_list_row<true>(band, s.draw_begin, s.draw_end, A.boxes, A.list_cnt[w], A.list_items, A.band_count, A.band_xr);
+    band_list_row<true>(band, s.draw_begin, s.draw_end, reinterpret_cast<const int4*>(A.boxes), 0u, A.list_cnt[w], A.list_items, A.band_count, A.band_xr);
   }
   if (t == 0) {
     A.out[1] = n_edges;
