@@ -803,6 +803,32 @@ Z2D_D uint32_t find_surface_by(const DevSurface* sfcs, uint32_t n_sfc, const uin
   return lo;
 }
 
+// One list item: draw i on tile row `band` (d, q: the two halves of its DrawBox).
+Z2D_D uint4 band_list_item(uint32_t i, int band, const int4 d, const int4 q, const uint32_t* __restrict__ band_off,
+                           const uint2* __restrict__ band_xr) {
+  uint32_t fl = (uint32_t)q.w, eb = 0u, nbe = 0u;
+  int tx0 = d.x, tx1 = d.y;
+  if (band >= q.x && band <= q.y) {
+    const uint32_t slot = (uint32_t)q.z + (uint32_t)(band - q.x);
+    eb = band_off[slot];
+    nbe = band_off[slot + 1] - eb;
+    fl |= kItemInRows;
+    if (!(fl & kItemSpecial)) {  // visit only the tile columns the edges of this row can touch
+      const uint2 xr = band_xr[slot];
+      tx0 = max(tx0, (int)(0x7fffffffu - xr.x));
+      tx1 = min(tx1, (int)xr.y - 1);
+    }
+  } else if (!(fl & kItemSpecial)) {
+    tx0 = 1;  // no edges on this tile row and nothing else to do there: never visited
+    tx1 = 0;
+  }
+  if (tx1 < tx0) {
+    tx0 = 0xffff;
+    tx1 = 0;
+  }
+  return make_uint4(i, (uint32_t)tx0 | ((uint32_t)tx1 << 16), eb, min(nbe, 0xffffffu) | (fl << 24));
+}
+
 // The draws [b, e) of one surface against one of its tile rows: count them (WRITE = false) or write their list items at o.
 // (`bx`: the boxes as int4 pairs, entry of draw i at bx[2 * (i - b0)]: global memory with b0 = 0, or a staged copy of [b, e))
 template <bool WRITE>
@@ -813,28 +839,7 @@ Z2D_D uint32_t band_list_row(int band, uint32_t b, uint32_t e, const int4* bx, u
       const int4 d = bx[2 * (i - b0)];  // {tx0, tx1, ty0, ty1}
       if (d.x >= 0 && band >= d.z && band <= d.w) {
         if (WRITE) {
-          const int4 q = bx[2 * (i - b0) + 1];  // {es0, es1, band_base, item_flags}
-          uint32_t fl = (uint32_t)q.w, eb = 0u, nbe = 0u;
-          int tx0 = d.x, tx1 = d.y;
-          if (band >= q.x && band <= q.y) {
-            const uint32_t slot = (uint32_t)q.z + (uint32_t)(band - q.x);
-            eb = band_off[slot];
-            nbe = band_off[slot + 1] - eb;
-            fl |= kItemInRows;
-            if (!(fl & kItemSpecial)) {  // visit only the tile columns the edges of this row can touch
-              const uint2 xr = band_xr[slot];
-              tx0 = max(tx0, (int)(0x7fffffffu - xr.x));
-              tx1 = min(tx1, (int)xr.y - 1);
-            }
-          } else if (!(fl & kItemSpecial)) {
-            tx0 = 1;  // no edges on this tile row and nothing else to do there: never visited
-            tx1 = 0;
-          }
-          if (tx1 < tx0) {
-            tx0 = 0xffff;
-            tx1 = 0;
-          }
-          items[o + n] = make_uint4(i, (uint32_t)tx0 | ((uint32_t)tx1 << 16), eb, min(nbe, 0xffffffu) | (fl << 24));
+          items[o + n] = band_list_item(i, band, d, bx[2 * (i - b0) + 1], band_off, band_xr);
         }
         n++;
       }
@@ -842,13 +847,16 @@ Z2D_D uint32_t band_list_row(int band, uint32_t b, uint32_t e, const int4* bx, u
     return n;
 }
 
+constexpr int kBandListWarps = 8;
 template <bool WRITE>
-__global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc, const uint32_t* __restrict__ work_base,
-                             const uint32_t* __restrict__ chunk_base, const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt,
-                             const uint32_t* __restrict__ off, uint4* __restrict__ items, const uint32_t* __restrict__ band_off,
-                             const uint2* __restrict__ band_xr) {
-  // one block per (surface, chunk of kDrawChunk draws); threads stride over the surface's tile-rows, so every thread of a
-  // warp reads the SAME box at the same time (one broadcast transaction instead of 32 strided ones)
+__global__ void __launch_bounds__(kBandListWarps * 32) k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc,
+                             const uint32_t* __restrict__ work_base, const uint32_t* __restrict__ chunk_base,
+                             const DrawBox* __restrict__ boxes, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
+                             uint4* __restrict__ items, const uint32_t* __restrict__ band_off, const uint2* __restrict__ band_xr) {
+  // blockIdx.x: (surface, chunk of kDrawChunk draws); blockIdx.y * 8 + warp: tile row.  A WARP per (chunk, tile row): its lanes
+  // test 32 boxes at a time (staged in shared memory), a ballot keeps the hits in draw order, and in the write pass the hits of a
+  // trip fetch their edge ranges and store their items side by side.  (A thread per tile row walking the 256 boxes one after the
+  // other, each hit followed by two dependent loads, was 30-170 us per pass whatever the batch size.)
   const uint32_t si = find_surface_by(sfcs, n_sfc, chunk_base, blockIdx.x);
   const DevSurface s = sfcs[si];
   const uint32_t n_draws = s.draw_end - s.draw_begin;
@@ -856,18 +864,28 @@ __global__ void k_band_lists(const DevSurface* __restrict__ sfcs, uint32_t n_sfc
   const uint32_t chunk = blockIdx.x - chunk_base[si];
   const uint32_t b = s.draw_begin + chunk * kDrawChunk;
   const uint32_t e = min(b + kDrawChunk, s.draw_end);
-  // the chunk's boxes go to shared memory first: every thread walks all of them, one dependent load per trip, and from
-  // global memory that was 250 ns per trip (66 us per pass whatever the batch size)
+  const int band0 = (int)blockIdx.y * kBandListWarps;
+  if (band0 >= s.tiles_y) return;
   __shared__ int4 s_box[2 * kDrawChunk];
   const int4* g_box = reinterpret_cast<const int4*>(boxes) + 2 * (size_t)b;
   for (uint32_t k = threadIdx.x; k < 2 * (e - b); k += blockDim.x) s_box[k] = __ldg(g_box + k);
   __syncthreads();
-  for (int band = (int)threadIdx.x; band < s.tiles_y; band += (int)blockDim.x) {
-    const uint32_t w = work_base[si] + (uint32_t)band * chunks + chunk;
-    const uint32_t o = WRITE ? off[w] : 0u;
-    const uint32_t n = band_list_row<WRITE>(band, b, e, s_box, b, o, items, band_off, band_xr);
-    if (!WRITE) cnt[w] = n;
+  const int band = band0 + (int)(threadIdx.x >> 5);
+  if (band >= s.tiles_y) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t w = work_base[si] + (uint32_t)band * chunks + chunk;
+  const uint32_t o = WRITE ? off[w] : 0u;
+  uint32_t n = 0;
+  for (uint32_t base = 0; base < e - b; base += 32) {
+    const uint32_t k = base + lane;
+    int4 d = make_int4(-1, 0, 0, 0);
+    if (k < e - b) d = s_box[2 * k];  // {tx0, tx1, ty0, ty1}
+    const bool hit = d.x >= 0 && band >= d.z && band <= d.w;
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (WRITE && hit) items[o + n + __popc(mask & ((1u << lane) - 1u))] = band_list_item(b + k, band, d, s_box[2 * k + 1], band_off, band_xr);
+    n += __popc(mask);
   }
+  if (!WRITE && lane == 0) cnt[w] = n;
 }
 template __global__ void k_band_lists<false>(const DevSurface*, uint32_t, const uint32_t*, const uint32_t*, const DrawBox*, uint32_t*,
                                              const uint32_t*, uint4*, const uint32_t*, const uint2*);
@@ -1149,13 +1167,11 @@ void launch_band_lists(bool write, const DevSurface* sfcs, uint32_t n_sfc, const
                        uint32_t n_chunks, const DrawBox* boxes, uint32_t* cnt, const uint32_t* off, uint4* items, const uint32_t* band_off,
                        const uint2* band_xr, uint32_t max_tiles_y, cudaStream_t st) {
   if (!n_chunks) return;
-  // a thread per tile row (a 4096-row canvas has 256): each walks the chunk's 256 boxes serially, and in the write pass follows
-  // every hit with two dependent loads, so the rows must not share threads (64 threads: 168 us on config 3; 256: see profiles)
-  const unsigned threads = max_tiles_y > 128 ? 256u : (max_tiles_y > 64 ? 128u : 64u);
+  const dim3 grid(n_chunks, (max_tiles_y + kBandListWarps - 1) / kBandListWarps);
   if (write)
-    k_band_lists<true><<<n_chunks, threads, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
+    k_band_lists<true><<<grid, kBandListWarps * 32, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
   else
-    k_band_lists<false><<<n_chunks, threads, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
+    k_band_lists<false><<<grid, kBandListWarps * 32, 0, st>>>(sfcs, n_sfc, work_base, chunk_base, boxes, cnt, off, items, band_off, band_xr);
 }
 void launch_edge_sim(const DevDraw* draws, uint32_t n_draws, const DevSurface* sfcs, const DevEdge* edges, const uint32_t* sp_off,
                      uint32_t* perm, int32_t* xs, int4* rows, cudaStream_t st) {
