@@ -275,7 +275,7 @@ def test_c5_scene_batch_sharding(cuda):
         return out
 
     whole = render(list(range(n_scenes)))
-    for s in (0, 5, 11):
+    for s in range(n_scenes):  # every scene against the oracle (fills, strokes through the unit stroker, gradient fills)
         assert np.array_equal(whole[s], render_scene(lib, scenes[s])), f"scene {s} differs from the oracle"
     all_sums = [sharding.surface_checksum(whole[s]) for s in range(n_scenes)]
     for world in (2, 4):
@@ -284,3 +284,22 @@ def test_c5_scene_batch_sharding(cuda):
             part = render(sharding.scenes_of_rank(n_scenes, world, rank))
             merged.update({s: sharding.surface_checksum(b) for s, b in part.items()})
         assert [merged[s] for s in range(n_scenes)] == all_sums
+
+
+def test_c5_more_scenes_match_the_oracle(cuda):
+    """64 further scenes of the config-5 generator (indices 1000 ...), rendered as ONE batch over 64 surfaces: integer work is
+    compared byte for byte; the gradient fills go through floating point, where the north star allows 1 LSB (none is used)."""
+    size, first, n = 1024, 1000, 64
+    scenes = [workloads.mixed_scene(first + k, size) for k in range(n)]
+    lib = load_oracle(fast=True)
+    sfcs = [Surface(Format.rgba, size, size, None, cuda) for _ in range(n)]
+    for sc, sfc in zip(scenes, sfcs):
+        _submit(cuda, sc, sfc)
+    got = [sfc.download().copy() for sfc in sfcs]
+    for sfc in sfcs:
+        sfc.deinit()
+    for k in range(n):
+        ref = render_scene(lib, scenes[k])
+        diff = np.abs(got[k].astype(np.int16) - ref.astype(np.int16))
+        assert int(diff.max()) <= 1, f"scene {first + k}: {int((diff > 1).sum())} bytes differ by more than 1 LSB"
+        assert int((diff != 0).sum()) == 0, f"scene {first + k}: {int((diff != 0).sum())} bytes differ by 1 LSB"
