@@ -1,7 +1,8 @@
 """The unit stroker (z2d_b200/csrc/stroke_units.cuh: walker -> units -> links) against the sub-path stroker (stroke.cuh), both
 compiled FOR THE HOST from the files the library compiles for the device (tools/stroke_units_host_test.cpp): the same multiset of
 edges for every sub-path of a random corpus, and the merged Pen vertex search against the reference's two-copy form
-(Pen.zig:138-232).  The sub-path stroker is the one every oracle / golden comparison of round 1 pinned; on the GPU both run under
+(Pen.zig:138-232), and the upper bound on a cubic's segment count that sizes the edge ranges of the single-pass fill
+flattening (geom.cuh curve_edge_bound) against Spline.decompose on 400 000 random and degenerate curves.  The sub-path stroker is the one every oracle / golden comparison of round 1 pinned; on the GPU both run under
 the same parity tests (Z2D_NO_STROKE_UNITS=1 selects the old one)."""
 import os
 import shutil
@@ -25,3 +26,4 @@ def test_unit_stroker_equals_subpath_stroker_on_host(tmp_path):
     run = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout[-2000:]
     assert " 0 mismatches" in run.stdout
+    assert "curve bound violated" not in run.stdout

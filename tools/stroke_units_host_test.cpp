@@ -5,6 +5,9 @@
 // of edges for every sub-path of a random corpus (open / closed polylines and Beziers, dashes incl. zero-length ones and
 // offsets, every cap / join, duplicate points, several move_tos per sub-path, identity / general / mirrored CTMs).
 //
+// Also checked here: the merged Pen vertex search of stroke.cuh against the reference's two-copy form, and the upper bound on a
+// cubic's segment count (geom.cuh curve_edge_bound, used by the single-pass fill flattening) against Spline.decompose.
+//
 //   g++ -O1 -std=c++17 -ffp-contract=off -I/usr/local/cuda/include -Iinclude tools/stroke_units_host_test.cpp -o /tmp/sut && /tmp/sut [n]
 #include <algorithm>
 #include <cmath>
@@ -334,6 +337,30 @@ int main(int argc, char** argv) {
     }
   }
   printf("%zu pen searches compared\n", pen_checks);
+  // ---- the edge bound of the single-pass fill flattening against Spline.decompose itself
+  size_t curve_checks = 0, bound_sum = 0, seg_sum = 0;
+  for (int t = 0; t < 400000; t++) {
+    const double span = t % 5 == 0 ? 4.0 : (t % 5 == 1 ? 4000.0 : 300.0);
+    Pt q[4];
+    for (int k = 0; k < 4; k++) q[k] = Pt{uni(0, span), uni(0, span)};
+    if (t % 11 == 0) q[1] = q[0];                       // degenerate control polygons
+    if (t % 13 == 0) q[2] = q[3];
+    if (t % 17 == 0) q[3] = q[0];                       // closed loop
+    if (t % 19 == 0) { q[1] = q[0]; q[2] = q[3]; }      // straight line (Spline.zig:39-42)
+    if (t % 23 == 0) { q[2] = Pt{q[0].x + 2 * (q[1].x - q[0].x), q[0].y + 2 * (q[1].y - q[0].y)}; }  // collinear
+    const double tol = t % 7 == 0 ? 0.001 : (t % 7 == 1 ? 1.5 : 0.1);
+    size_t segs = 0;
+    spline_decompose(q[0], q[1], q[2], q[3], tol * tol, [&](Pt) { segs++; });
+    const uint32_t bound = curve_edge_bound(q[0], q[1], q[2], q[3], tol);
+    curve_checks++;
+    bound_sum += bound;
+    seg_sum += segs;
+    if (segs > bound) {
+      if (bad < 20) printf("curve bound violated: %zu segments, bound %u (tol %g)\n", segs, bound, tol);
+      bad++;
+    }
+  }
+  printf("%zu curves: bound / segments = %.2f\n", curve_checks, (double)bound_sum / (double)seg_sum);
   printf("%d cases, %zu edges, %zu units, %zu links: %d mismatches\n", n_cases, total_edges, total_units, total_links, bad);
   return bad ? 1 : 0;
 }

@@ -137,4 +137,22 @@ Z2D_D void spline_decompose(Pt a, Pt b, Pt c, Pt d, double tol_sq, F&& line_to) 
   line_to(d);
 }
 
+// Upper bound on the number of line segments Spline.decompose yields for a cubic (the single-pass flattening of kernels.cu
+// sizes a curve's edge range with it; tools/stroke_units_host_test.cpp checks it against the subdivision on random curves).
+// With M = max |second difference| of the control polygon, Knots.errorSq <= M^2, and a de Casteljau halving divides second
+// differences by 4, so no piece is split beyond depth k = min{k : M^2 / 16^k < tol^2}.
+Z2D_D uint32_t curve_edge_bound(Pt a, Pt b, Pt c, Pt e, double tol) {
+  if (pt_eq(a, b) && pt_eq(c, e)) return 1u;  // Spline.zig:39-42
+  const double d0x = a.x - 2.0 * b.x + c.x, d0y = a.y - 2.0 * b.y + c.y;
+  const double d1x = b.x - 2.0 * c.x + e.x, d1y = b.y - 2.0 * c.y + e.y;
+  const double m0 = d0x * d0x + d0y * d0y, m1 = d1x * d1x + d1y * d1y;
+  double ratio = (m0 > m1 ? m0 : m1) / (tol * tol) * 1.01;  // (1 % for the rounding of the halving arithmetic)
+  uint32_t k = 0;
+  while (ratio >= 1.0 && k < 20u) {
+    ratio *= 0.0625;
+    k++;
+  }
+  return 1u << k;
+}
+
 }  // namespace z2d

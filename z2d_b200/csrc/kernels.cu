@@ -367,20 +367,6 @@ __global__ void k_flatten_nodes(const DevSubPath* __restrict__ sps, const uint32
 // edges, and mark the rest of the range dead (edge_draw = ~0, skipped by binning).  Extents come from the same pass, so K2
 // runs after it.  A node that would exceed its bound (NaN / infinite coordinates) raises ctr[4] and the batch is redone by
 // the two-pass kernels.
-Z2D_D uint32_t curve_edge_bound(Pt a, Pt b, Pt c, Pt e, double tol) {
-  if (pt_eq(a, b) && pt_eq(c, e)) return 1u;  // Spline.zig:39-42
-  const double d0x = a.x - 2.0 * b.x + c.x, d0y = a.y - 2.0 * b.y + c.y;
-  const double d1x = b.x - 2.0 * c.x + e.x, d1y = b.y - 2.0 * c.y + e.y;
-  const double m0 = d0x * d0x + d0y * d0y, m1 = d1x * d1x + d1y * d1y;
-  double ratio = (m0 > m1 ? m0 : m1) / (tol * tol) * 1.01;  // (1 % for the rounding of the halving arithmetic)
-  uint32_t k = 0;
-  while (ratio >= 1.0 && k < 20u) {
-    ratio *= 0.0625;
-    k++;
-  }
-  return 1u << k;
-}
-
 __global__ void k_node_bounds(const DevSubPath* __restrict__ sps, const uint32_t* __restrict__ node_sp, uint32_t n_nodes,
                               const z2d_node* __restrict__ nodes, const DevDraw* __restrict__ draws, uint32_t* __restrict__ counts,
                               uint32_t* __restrict__ curve_list, uint32_t* __restrict__ n_curves) {
