@@ -12,7 +12,14 @@ HEADERS = ["kernels.cuh", "z2d_batch.cuh", "z2d_device.cuh", "raster.cuh", "patt
 # -fmad=false: the reference never fuses a*b+c and its results (f64 edge crossings,
 # f32 blend arithmetic) are reproduced bit-exactly only without contraction.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--split-compile", "0", "-t", "0"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+# Every translation unit is compiled on its own with an EXPLICIT --split-compile count.  The count decides how NVVM partitions a
+# unit's functions before optimising, and with it the generated code: "0" (= the build machine's core count, shared between the
+# units of one nvcc command) made the K4 kernels come out differently -- and up to 14 % slower -- whenever an unrelated file or
+# flag changed.  raster.cu is compiled unsplit (the fastest of the versions measured: config 3 raster 6.40 ms against 6.88 ms
+# with 4, config 2 2.29 against 2.34 ms), the others with fixed counts so that their code does not depend on the machine either.
+SPLIT = {"kernels.cu": os.environ.get("Z2D_KERNELS_SPLIT", "8"), "raster.cu": os.environ.get("Z2D_RASTER_SPLIT", "1"), "z2d_lib.cu": "4"}
+BUILD_DIR = os.path.join(HERE, "_build")
 
 
 def needs_build():
@@ -22,19 +29,42 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), so=None):
+    so = so or SO
+    if not force and not extra and so == SO and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    tag = os.path.splitext(os.path.basename(so))[0]
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(BUILD_DIR, f"{tag}.{os.path.splitext(src)[0]}.o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["--split-compile", SPLIT[src]] + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    failed = False
+    for src, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out + err)
+            failed = True
+        elif verbose:
+            sys.stderr.write(err)
+    if failed:
+        raise RuntimeError("nvcc failed building libz2d_cuda.so")
+    res = subprocess.run([nvcc, "-shared", "-cudart", "static", "-o", so] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libz2d_cuda.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
-    return SO
+        raise RuntimeError("nvcc failed linking libz2d_cuda.so")
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m z2d_b200.build [--force] [-v] [--variant NAME -DFOO=1 ...]  (variants: z2d_b200/variants/NAME.so, tools/build_variant.sh)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+        print(build(force=True, extra=sys.argv[i + 2:], so=os.path.join(HERE, "variants", sys.argv[i + 1] + ".so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -66,6 +66,7 @@ void launch_node_bounds(const DevSubPath* sps, uint32_t n_sp, uint32_t* node_sp,
 void launch_flatten_nodes_pool(const DevSubPath* sps, const uint32_t* node_sp, uint32_t n_nodes, const z2d_node* nodes, DevDraw* draws,
                                const uint32_t* node_offs, uint32_t* ctr, DevEdge* edges, uint32_t* edge_draw, uint32_t edge_cap,
                                const uint32_t* curve_list, cudaStream_t st);
+void raster_preload();  // raster.cu: loads the K4 kernels (call once per process, before other kernels are used)
 // unit stroker (stroke_units.cuh) for the sub-paths flagged kSpStrokeUnits: walker -> units -> links.  ctr[0..2] = units, links and
 // edge slots taken (they run past the capacities when those are too small: the caller enlarges and repeats).
 constexpr size_t kStrokeUnitBytes = 64, kStrokeLinkBytes = 16, kStrokePortBytes = 64;  // per unit / link / unit

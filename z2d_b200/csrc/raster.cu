@@ -8,6 +8,16 @@
 
 namespace z2d {
 
+// Load the two kernels before anything else of the library.  With lazy module loading a kernel's code is placed when it is
+// first used, i.e. behind whatever was launched before it, and K4's speed was seen to depend on that placement (6.85 vs 7.8 ms on
+// config 3 for the same SASS, flipping whenever an unrelated kernel changed size).  Loaded first, at context creation, its
+// placement no longer depends on the other kernels.
+void raster_preload() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_raster_tiles);
+  cudaFuncGetAttributes(&a, k_raster_tiles_rich);
+}
+
 void launch_raster(const RasterArgs& A, bool rich, cudaStream_t st) {
   if (!A.n_tiles) return;
   const unsigned blocks = (unsigned)((A.n_tiles + kRasterThreads / 32 - 1) / (kRasterThreads / 32));

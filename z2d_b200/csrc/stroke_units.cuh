@@ -713,7 +713,10 @@ struct PoolSink {  // Polygon.addEdge into pool slots; horizontal edges leave a 
   }
 };
 
-__global__ void __launch_bounds__(128) k_stroke_units(const StrokeUnit* __restrict__ units, uint32_t unit_cap, uint32_t* __restrict__ ctr,
+#ifndef Z2D_UNITS_MIN_CTAS
+#define Z2D_UNITS_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(128, Z2D_UNITS_MIN_CTAS) k_stroke_units(const StrokeUnit* __restrict__ units, uint32_t unit_cap, uint32_t* __restrict__ ctr,
                                                       DevDraw* __restrict__ draws, const PenV* __restrict__ pens,
                                                       const double* __restrict__ dashes, Pt* __restrict__ ports,
                                                       DevEdge* __restrict__ edges, uint32_t* __restrict__ edge_draw, uint32_t edge_cap) {

@@ -1337,6 +1337,7 @@ int32_t z2d_ctx_create(int32_t device, void* stream, z2d_ctx** out) {
   cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
   for (InputSet& is : c->in) cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming);
+  if (getenv("Z2D_NO_RASTER_PRELOAD") == nullptr) raster_preload();
   c->small_enabled = getenv("Z2D_NO_SMALL_BATCH") == nullptr;
   c->stroke_units = getenv("Z2D_NO_STROKE_UNITS") == nullptr;
   c->fill_single_pass = getenv("Z2D_NO_FILL_SINGLE_PASS") == nullptr;
