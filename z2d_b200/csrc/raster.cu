@@ -1,6 +1,8 @@
-// K4 (raster.cuh) as its own translation unit.  The two raster kernels are ~300 / ~530 KB of SASS and instruction-fetch
-// sensitive: compiled together with the other kernels, ptxas scheduled them differently whenever an unrelated kernel changed
-// (6.85 vs 7.87 ms on config 3 for byte-identical raster source).  On their own, their code only changes when they do.
+// K4 (raster.cuh) as its own translation unit.  The two raster kernels are ~300 / ~540 KB of SASS and instruction-fetch
+// sensitive, and their code depends on how NVVM partitions a unit's functions under --split-compile: built together with the
+// other kernels and "--split-compile 0" they came out differently (6.4 ... 7.9 ms on config 3 for byte-identical raster source)
+// whenever an unrelated kernel or flag changed.  On their own, compiled unsplit (z2d_b200/build.py), their code only changes
+// when they do.
 #define Z2D_RASTER_TU 1
 #include "kernels.cuh"
 #include "pattern.cuh"
@@ -8,10 +10,8 @@
 
 namespace z2d {
 
-// Load the two kernels before anything else of the library.  With lazy module loading a kernel's code is placed when it is
-// first used, i.e. behind whatever was launched before it, and K4's speed was seen to depend on that placement (6.85 vs 7.8 ms on
-// config 3 for the same SASS, flipping whenever an unrelated kernel changed size).  Loaded first, at context creation, its
-// placement no longer depends on the other kernels.
+// Load the two kernels at context creation instead of at the first batch (lazy module loading would otherwise add the load of
+// ~840 KB of code to the first draw call's latency).
 void raster_preload() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_raster_tiles);
