@@ -54,6 +54,9 @@ def build(force=False, verbose=False, extra=(), so=None):
     if failed:
         raise RuntimeError("nvcc failed building libz2d_cuda.so")
     res = subprocess.run([nvcc, "-shared", "-cudart", "static", "-o", so] + objs, capture_output=True, text=True)
+    for obj in objs:  # (nothing is incremental here, and the objects would travel with every gpurun snapshot)
+        if os.path.exists(obj):
+            os.remove(obj)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking libz2d_cuda.so")
