@@ -265,7 +265,8 @@ int32_t z2d_surface_put_pixel(z2d_sfc* sfc, int32_t x, int32_t y, const z2d_pixe
  * Flushes + syncs (a 4-byte read-back). */
 int32_t z2d_surface_get_pixel(z2d_sfc* sfc, int32_t x, int32_t y, z2d_pixel* out);
 
-/* painter.fill (painter.zig:66-143) */
+/* painter.fill (painter.zig:66-143).  Node coordinates must be finite: with a NaN or infinite control point the reference's
+ * Spline.decompose recurses without bound, and so, in effect, does the subdivision here (known limits). */
 int32_t z2d_fill(z2d_ctx* ctx, z2d_sfc* sfc, const z2d_pattern* pattern,
                  const z2d_node* nodes, size_t n_nodes, const z2d_fill_opts* opts);
 
