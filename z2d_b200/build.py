@@ -13,12 +13,14 @@ HEADERS = ["kernels.cuh", "z2d_batch.cuh", "z2d_device.cuh", "raster.cuh", "patt
 # f32 blend arithmetic) are reproduced bit-exactly only without contraction.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
-# Every translation unit is compiled on its own with an EXPLICIT --split-compile count.  The count decides how NVVM partitions a
+# Every translation unit is compiled on its own, UNSPLIT (--split-compile 1).  The split count decides how NVVM partitions a
 # unit's functions before optimising, and with it the generated code: "0" (= the build machine's core count, shared between the
 # units of one nvcc command) made the K4 kernels come out differently -- and up to 14 % slower -- whenever an unrelated file or
-# flag changed.  raster.cu is compiled unsplit (the fastest of the versions measured: config 3 raster 6.40 ms against 6.88 ms
-# with 4, config 2 2.29 against 2.34 ms), the others with fixed counts so that their code does not depend on the machine either.
-SPLIT = {"kernels.cu": os.environ.get("Z2D_KERNELS_SPLIT", "8"), "raster.cu": os.environ.get("Z2D_RASTER_SPLIT", "1"), "z2d_lib.cu": "4"}
+# flag changed, and with a fixed count > 1 two builds of the same source still differed in kernels.cu (the partition depends on
+# thread timing).  Unsplit builds are reproducible bit for bit (checked: SASS of two builds identical) and were the fastest K4
+# measured (config 3 raster 6.40 ms against 6.88 ms with a 4-way split, config 2 2.29 against 2.34 ms); kernels.cu takes 3.5
+# minutes this way.  Z2D_*_SPLIT override the counts for experiments.
+SPLIT = {"kernels.cu": os.environ.get("Z2D_KERNELS_SPLIT", "1"), "raster.cu": os.environ.get("Z2D_RASTER_SPLIT", "1"), "z2d_lib.cu": "1"}
 BUILD_DIR = os.path.join(HERE, "_build")
 
 
